@@ -1,0 +1,221 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU (build container only).
+
+    python oracle/refgen/make_golden.py [--only masks|unet_small|ddim|unet_full] [--check-oracle]
+
+The reference has no tests or golden vectors of its own; these files are outputs of the
+reference's own code (imported from /root/reference by ref_harness.py) on seeded synthetic inputs that
+the tests regenerate with camc2v_b200.synth.  With --check-oracle every golden is also compared with
+oracle/ on the spot and the deviation printed (recorded in DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_harness as rh  # noqa: E402
+from camc2v_b200 import synth  # noqa: E402
+from camc2v_b200.config import UNetConfig  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+TRAJ = ["pan_yaw", "stationary", "dolly", "yaw", "roll_pan_up", "orbit"]
+SMALL_UNET = dict(model_channels=64)
+SMALL_CFG = UNetConfig(model_channels=64, origin_h=128, origin_w=128)
+SMALL_HW = 16
+PERTURB_SEED = 123
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm()), float((a - b).abs().max() / b.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------
+def ref_camera(model, K, w2c, cond_idx, H, W, resolutions):
+    """The geometry half of get_batch_input_camera_condition_process (camcontexti2v.py:525-554), calling
+    the reference's own methods in the reference's order."""
+    with torch.no_grad():
+        c2w = w2c.float().inverse()
+        rel = model.get_relative_pose(c2w, cond_idx, mode="left", normalize_T0=False)
+        rel[:, :, :3, 3] = rel[:, :, :3, 3] * 1.0
+        pairs = model.get_relative_c2w_RT_pairs(rel)
+        R = pairs[..., :3, :3]
+        t = pairs[..., :3, 3:4]
+        t = model.add_small_perturbation(t, epsilon=1e-6)
+        F = model.get_fundamental_matrix(K.float().unsqueeze(1), R, t)
+        T = w2c.shape[1]
+        masks = {int(8 * ds): model.get_epipolar_mask(F, T, H // int(8 * ds), W // int(8 * ds), int(8 * ds)) for ds in resolutions}
+        return rel, F, masks
+
+
+def gen_masks(model, check):
+    import oracle
+    from oracle import camera_oracle
+
+    out = {}
+    for kind in TRAJ:
+        K, w2c = synth.synth_camera(kind, T=16, H=256, W=256, B=1)
+        cond = torch.zeros(1, dtype=torch.long)
+        torch.manual_seed(PERTURB_SEED)
+        rel, F, masks = ref_camera(model, K, w2c, cond, 256, 256, (8, 4, 2, 1))
+        out[f"{kind}.F"] = F.numpy()
+        out[f"{kind}.rel_c2w"] = rel.numpy()
+        for d, m in masks.items():
+            mn = m.numpy()
+            packed = np.packbits(mn, axis=-1)
+            out[f"{kind}.d{d}.sha256"] = np.frombuffer(bytes.fromhex(sha(packed)), dtype=np.uint8)
+            out[f"{kind}.d{d}.rowsum"] = mn.sum(-1).astype(np.int32)
+            out[f"{kind}.d{d}.colsum"] = mn.sum(-2).astype(np.int32)
+            if d >= 32:
+                out[f"{kind}.d{d}.packed"] = packed
+            print(f"  mask {kind} d={d} shape={tuple(mn.shape)} density={mn.mean():.4f}")
+        pl = model.ray_condition(K.float(), rel, 256, 256, "cpu")
+        out[f"{kind}.plucker_sub"] = pl[..., 3::8, 3::8].numpy()
+        model.camera_embedding = "ray"
+        ry = model.ray_condition(K.float(), rel, 256, 256, "cpu")
+        model.camera_embedding = "plucker"
+        out[f"{kind}.ray_sub"] = ry[..., 3::8, 3::8].numpy()
+        if check:
+            torch.manual_seed(PERTURB_SEED)
+            F2, m2, rel2 = camera_oracle.camera_condition_masks(K, w2c, cond)
+            print(f"    oracle: F bit-equal={torch.equal(F2, F)} rel bit-equal={torch.equal(rel2, rel)}", end="")
+            for d in masks:
+                print(f" d{d}:mismatch={(m2[d] != masks[d]).sum().item()}", end="")
+            p2 = oracle.plucker(K, rel, 256, 256)
+            print(f" plucker maxabs={float((p2 - pl).abs().max()):.2e}")
+    np.savez_compressed(os.path.join(GOLD, "masks.npz"), **out)
+
+
+# ---------------------------------------------------------------------------------------------
+def synth_inputs(cfg: UNetConfig, hw: int, n_ctx_frames: int, tag: str, B: int = 1, seed: int = 7):
+    """Seeded inputs of one UNet pass (regenerated identically by the tests)."""
+    T = cfg.temporal_length
+    mc = cfg.model_channels
+    x = synth.synth_tensor(f"{tag}.x", (B, 4, T, hw, hw), seed)
+    c_concat = synth.synth_tensor(f"{tag}.c_concat", (B, 4, T, hw, hw), seed)
+    ctx_cond = synth.synth_tensor(f"{tag}.ctx_cond", (B, 77 + 256 * (1 + n_ctx_frames), cfg.context_dim), seed)
+    ctx_uncond = synth.synth_tensor(f"{tag}.ctx_uncond", (B, 77 + 256, cfg.context_dim), seed)
+    chans = [mc * m for m in cfg.channel_mult]
+    pf = [synth.synth_tensor(f"{tag}.pluker{i}", (B, c, T, hw >> i, hw >> i), seed, std=0.1) for i, c in enumerate(chans)]
+    return dict(x=x, c_concat=c_concat, ctx_cond=ctx_cond, ctx_uncond=ctx_uncond, pluker=pf,
+                fs=torch.full((B,), 3, dtype=torch.long))
+
+
+def build_ref(unet_overrides, origin):
+    model = rh.build_reference_model(unet_overrides=unet_overrides)
+    if origin is not None:
+        for m in model.model.diffusion_model.modules():
+            if m.__class__.__name__ == "Epipolar":
+                m.origin_h = m.origin_w = origin
+    synth.fill_module_(model.model.diffusion_model, seed=0)
+    return model
+
+
+def camera_condition(model, hw_img, kind, pluker):
+    K, w2c = synth.synth_camera(kind, T=16, H=hw_img, W=hw_img, B=1)
+    torch.manual_seed(PERTURB_SEED)
+    rel, F, masks = ref_camera(model, K, w2c, torch.zeros(1, dtype=torch.long), hw_img, hw_img, (8, 4, 2, 1))
+    return {"pluker_embedding_features": pluker, "sample_locs_dict": masks,
+            "cond_frame_index": torch.zeros(1, dtype=torch.long), "add_type": "add_to_main_branch"}, F
+
+
+def gen_unet_small(check):
+    model = build_ref(SMALL_UNET, 128)
+    unet = model.model.diffusion_model
+    inp = synth_inputs(SMALL_CFG, SMALL_HW, 2, "small")
+    cam, F = camera_condition(model, 8 * SMALL_HW, "pan_yaw", inp["pluker"])
+    out = {"F": F.numpy()}
+    t = torch.full((1,), 599, dtype=torch.long)
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    with torch.no_grad():
+        y_c = unet(xc, t, context=inp["ctx_cond"], fs=inp["fs"], camera_condition=cam)
+        y_u = unet(xc, t, context=inp["ctx_uncond"], fs=inp["fs"], camera_condition=cam)
+        y_n = unet(xc, t, context=inp["ctx_cond"], fs=inp["fs"], camera_condition=None)
+    out.update(y_cond=y_c.numpy(), y_uncond=y_u.numpy(), y_nocam=y_n.numpy())
+    print(f"  small unet: out std {y_c.std():.4f} / {y_u.std():.4f} / {y_n.std():.4f}")
+
+    # one full CFG step through the reference's own sampler (ddim.py:241-346)
+    DDIM = rh.patch_ddim_for_cpu()
+    sampler = DDIM(model)
+    sampler.make_schedule(25, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
+    for k in ("ddim_timesteps", "ddim_alphas", "ddim_alphas_prev", "ddim_sigmas", "ddim_sqrt_one_minus_alphas"):
+        out["sched." + k] = np.asarray(getattr(sampler, k), dtype=np.float64 if k == "ddim_timesteps" else np.float32)
+    out["sched.alphas_cumprod"] = model.alphas_cumprod.numpy()
+    cond = {"c_crossattn": [inp["ctx_cond"]], "c_concat": [inp["c_concat"]], "camera_condition": cam}
+    uc = {"c_crossattn": [inp["ctx_uncond"]], "c_concat": [inp["c_concat"]]}
+    index = 14
+    step = int(sampler.ddim_timesteps[index])
+    ts = torch.full((1,), step, dtype=torch.long)
+    torch.manual_seed(20230211)
+    x_prev, pred_x0 = sampler.p_sample_ddim(inp["x"], cond, ts, index=index, unconditional_guidance_scale=3.5,
+                                            unconditional_conditioning=uc, guidance_rescale=0.7, fs=inp["fs"],
+                                            enable_camera_condition=True)
+    out.update(step_x_prev=x_prev.numpy(), step_pred_x0=pred_x0.numpy(), step_index=np.int64(index), step_t=np.int64(step))
+    np.savez_compressed(os.path.join(GOLD, "unet_small.npz"), **out)
+
+    if check:
+        from oracle.unet_oracle import UNetOracle
+        orc = UNetOracle(unet.state_dict(), SMALL_CFG)
+        for name, ctx, c, ref in (("cond", inp["ctx_cond"], cam, y_c), ("uncond", inp["ctx_uncond"], cam, y_u), ("nocam", inp["ctx_cond"], None, y_n)):
+            y = orc.forward(xc, t, ctx, inp["fs"], c)
+            print(f"    oracle vs reference [{name}]: rel-L2 {rel_err(y, ref)[0]:.3e}  max|err|/max|ref| {rel_err(y, ref)[1]:.3e}")
+
+
+def gen_unet_full(check):
+    cfg = UNetConfig()
+    t0 = time.time()
+    model = build_ref(None, None)
+    unet = model.model.diffusion_model
+    print(f"  full model built+filled in {time.time() - t0:.0f}s")
+    inp = synth_inputs(cfg, 32, 2, "full")
+    cam, F = camera_condition(model, 256, "pan_yaw", inp["pluker"])
+    t = torch.full((1,), 599, dtype=torch.long)
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    out = {"F": F.numpy()}
+    with torch.no_grad():
+        t0 = time.time()
+        y_c = unet(xc, t, context=inp["ctx_cond"], fs=inp["fs"], camera_condition=cam)
+        print(f"  reference cond pass {time.time() - t0:.1f}s  out std {y_c.std():.4f}")
+        t0 = time.time()
+        y_u = unet(xc, t, context=inp["ctx_uncond"], fs=inp["fs"], camera_condition=cam)
+        print(f"  reference uncond pass {time.time() - t0:.1f}s")
+    out.update(y_cond=y_c.numpy(), y_uncond=y_u.numpy())
+    np.savez_compressed(os.path.join(GOLD, "unet_full.npz"), **out)
+    if check:
+        from oracle.unet_oracle import UNetOracle
+        orc = UNetOracle(unet.state_dict(), cfg)
+        t0 = time.time()
+        y = orc.forward(xc, t, inp["ctx_cond"], inp["fs"], cam)
+        print(f"    oracle cond pass {time.time() - t0:.1f}s; vs reference rel-L2 {rel_err(y, y_c)[0]:.3e} max-norm {rel_err(y, y_c)[1]:.3e}")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--check-oracle", action="store_true")
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    if a.only in (None, "masks"):
+        print("[masks]")
+        gen_masks(rh.build_reference_model(unet_overrides=SMALL_UNET), a.check_oracle)
+    if a.only in (None, "unet_small", "ddim"):
+        print("[unet_small + ddim step]")
+        gen_unet_small(a.check_oracle)
+    if a.only in ("unet_full",):
+        print("[unet_full]")
+        gen_unet_full(a.check_oracle)

@@ -1,0 +1,157 @@
+"""Harness that imports the UNMODIFIED reference (LDenninger/CamC2V) from /root/reference on CPU.
+
+TEST INFRASTRUCTURE ONLY.  It is used (a) to pin `oracle/` against the reference's own code and
+(b) to generate the golden vectors committed under `tests/golden/` (see `make_golden.py`).
+It cannot run on the GPU box (`/root/reference` does not exist there) and nothing in the
+product path (`camc2v_b200/`), `bench.py` or the `-m gpu` tests imports it.
+
+What it does:
+  * installs a ~20-line stub `pytorch_lightning` (absent in this image) so that
+    `model.camcontexti2v` -> `model.base` -> `lvdm.models.ddpm3d` import;
+  * loads `configs/models/camcontexti2v_256.yaml` with `yaml.safe_load` into an attribute-dict;
+  * replaces the three frozen third-party stages (VAE, CLIP text, CLIP image) by `torch.nn.Identity`
+    and the pose encoder (needs `diffusers`, absent) by None;
+  * constructs `model.camcontexti2v.CamContextI2V`, which applies the reference's own monkey patches
+    (camcontexti2v.py:111-170), then adds `pluker_projection` exactly as camcontexti2v.py:151-156
+    would have done had a pose encoder been configured;
+  * overrides `DDIMSampler.register_buffer` (ddim.py:18-22 hard-codes `.to("cuda")`).
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+import yaml
+
+REF_ROOT = os.environ.get("CAMC2V_REFERENCE", "/root/reference")
+REF_PKG = os.path.join(REF_ROOT, "CamContextI2V")
+REF_CFG = os.path.join(REF_ROOT, "configs")
+
+
+class AttrDict(dict):
+    """dict with attribute access + hasattr/setattr, enough for the reference's OmegaConf usage."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __deepcopy__(self, memo):
+        return AttrDict({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+
+def to_attr(o):
+    if isinstance(o, dict):
+        return AttrDict({k: to_attr(v) for k, v in o.items()})
+    if isinstance(o, list):
+        return [to_attr(v) for v in o]
+    return o
+
+
+def _install_pl_stub():
+    if "pytorch_lightning" in sys.modules:
+        return
+    pl = types.ModuleType("pytorch_lightning")
+
+    class LightningModule(nn.Module):
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+        def log(self, *a, **k):
+            pass
+
+        def log_dict(self, *a, **k):
+            pass
+
+    class LightningDataModule:
+        pass
+
+    def seed_everything(seed, *a, **k):
+        torch.manual_seed(seed)
+        return seed
+
+    pl.LightningModule = LightningModule
+    pl.LightningDataModule = LightningDataModule
+    pl.seed_everything = seed_everything
+    util = types.ModuleType("pytorch_lightning.utilities")
+    util.rank_zero_only = lambda f: f
+    pl.utilities = util
+    sys.modules["pytorch_lightning"] = pl
+    sys.modules["pytorch_lightning.utilities"] = util
+
+
+def setup_reference_imports():
+    if not os.path.isdir(REF_PKG):
+        raise RuntimeError(f"reference not found at {REF_PKG}")
+    _install_pl_stub()
+    if REF_PKG not in sys.path:
+        sys.path.insert(0, REF_PKG)
+
+
+def load_model_config(name="models/camcontexti2v_256.yaml"):
+    with open(os.path.join(REF_CFG, name)) as f:
+        cfg = yaml.safe_load(f)
+    return to_attr(cfg["model"])
+
+
+IDENTITY = {"target": "torch.nn.Identity"}
+
+
+def build_reference_model(unet_overrides: dict | None = None, seed: int = 0):
+    """Construct the reference CamContextI2V (UNet + patches + Epipolar + pluker_projection) on CPU.
+
+    unet_overrides: optional overrides of unet_config.params (e.g. a small model_channels for fast tests).
+    """
+    setup_reference_imports()
+    from model.camcontexti2v import CamContextI2V  # noqa
+
+    mc = load_model_config()
+    p = mc.params
+    p.first_stage_config = to_attr(IDENTITY)
+    p.cond_stage_config = to_attr(IDENTITY)
+    p.img_cond_stage_config = to_attr(IDENTITY)
+    p.image_proj_stage_config = to_attr(IDENTITY)
+    p.pose_encoder_config = None
+    # The 46.5 M adaptor is once-per-sample (SURVEY f-1) and not on the per-step path.
+    p.multi_cond_strategy = None
+    p.pop("multi_latent_adaptor", None)
+    if unet_overrides:
+        for k, v in unet_overrides.items():
+            p.unet_config.params[k] = v
+    torch.manual_seed(seed)
+    try:
+        model = CamContextI2V(**p)
+    except TypeError:
+        raise
+    model.eval()
+    unet = model.model.diffusion_model
+    # camcontexti2v.py:151-156: pluker_projection is only added when a pose encoder exists.
+    for _name, _module in unet.named_modules():
+        if _module.__class__.__name__ == "BasicTransformerBlock" and hasattr(_module, "epipolar"):
+            c = _module.attn1.to_k.in_features
+            if not hasattr(_module, "pluker_projection"):
+                _module.add_module("pluker_projection", nn.Linear(c, c))
+    return model
+
+
+def patch_ddim_for_cpu():
+    setup_reference_imports()
+    from lvdm.models.samplers.ddim import DDIMSampler
+
+    def register_buffer(self, name, attr):
+        setattr(self, name, attr)
+
+    DDIMSampler.register_buffer = register_buffer
+    return DDIMSampler
