@@ -1,0 +1,102 @@
+"""ctypes binding of libcamc2v_b200.so (the C ABI declared in include/camc2v_b200.h).
+
+The product path has NO fallback: if the shared object is missing or a call fails, an exception is
+raised.  Build it with `python -m camc2v_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcamc2v_b200.so")
+
+A_PLAIN, A_CONV2D, A_CONVT = 0, 1, 2
+EPI_LINEAR, EPI_GEGLU = 0, 1
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("rowbias", C.c_void_p),
+        ("residual", C.c_void_p), ("out", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("Cin", C.c_int), ("taps", C.c_int),
+        ("a_mode", C.c_int), ("nb", C.c_int), ("d1", C.c_int), ("d2", C.c_int),
+        ("lda", C.c_int), ("rows_per_group", C.c_int), ("ldr", C.c_int), ("ldo", C.c_int),
+        ("out_bf16", C.c_int), ("epi", C.c_int),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("bq", C.c_int), ("lq", C.c_int), ("lk", C.c_int), ("heads", C.c_int),
+        ("ldq", C.c_int), ("ldk", C.c_int), ("ldv", C.c_int), ("ldo", C.c_int),
+        ("q_bstride", C.c_int64), ("k_bstride", C.c_int64), ("v_bstride", C.c_int64), ("o_bstride", C.c_int64),
+        ("kv_div", C.c_int), ("out_scale", C.c_float), ("accumulate", C.c_int),
+        ("k2", C.c_void_p), ("v2", C.c_void_p), ("lk2", C.c_int), ("ldk2", C.c_int), ("ldv2", C.c_int),
+        ("epi_F", C.c_void_p), ("epi_T", C.c_int), ("epi_H", C.c_int), ("epi_W", C.c_int), ("epi_d", C.c_int),
+        ("mask", C.c_void_p), ("mask_bstride", C.c_int64),
+    ]
+
+
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> (restype, argtypes); must list every symbol of include/camc2v_b200.h (tests/test_abi.py checks).
+PROTOTYPES = {
+    "c2v_abi_version": (_i, []),
+    "c2v_status_string": (C.c_char_p, [_i]),
+    "c2v_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
+    "c2v_gemm_tile_n": (_i, [_i, _i]),
+    "c2v_skinny_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "c2v_timestep_embedding": (_i, [_vp, _vp, _i, _i, _vp]),
+    "c2v_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
+    "c2v_groupnorm_ws_floats": (_i64, [_i, _i, _i]),
+    "c2v_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "c2v_attention": (_i, [C.POINTER(AttnDesc), _vp]),
+    "c2v_attention_temporal": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "c2v_epipolar_mask": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "c2v_plucker": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "c2v_to_channels_last": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "c2v_from_channels_last": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "c2v_concat_channels": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "c2v_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "c2v_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "c2v_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "c2v_copy_rows": (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _vp]),
+    "c2v_cfg_ddim_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _f, _f, _vp]),
+}
+
+_lib = None
+LAUNCHES = 0   # number of kernel-launching C-ABI calls issued by this process (bench.py reports it)
+
+
+class C2VError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared object (once).  Raises if it has not been built: there is no CPU/torch fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise C2VError(f"{LIB_PATH} not found: build it with `python -m camc2v_b200.build` "
+                           "(the camc2v_b200 product path has no fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().c2v_status_string(status).decode()
+        raise C2VError(f"{what} failed: {msg} (status {status})")
+
+
+def call(name: str, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    check(getattr(load(), name)(*args), name)

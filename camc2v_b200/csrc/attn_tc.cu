@@ -1,0 +1,367 @@
+// Flash-style attention on tcgen05 tensor cores, head dim 64, bf16 operands, fp32 softmax.
+//   replaces xformers.ops.memory_efficient_attention (R/lvdm/modules/attention.py:177,189), the einsum
+//   softmax path (attention.py:105-129) and F.scaled_dot_product_attention with the boolean epipolar mask
+//   (R/model/modules/epipolar.py:99).
+//
+// One CTA = 128 query rows of one (batch, head).  Per 128-key tile:
+//     S = Q K^T          tcgen05.mma 128x128x16 (x4), both operands K-major in 128B-swizzled smem (TMA)
+//     P = softmax tile   4 warps, one query row per thread, S read from TMEM in two passes (max, then exp)
+//     O += P V           tcgen05.mma 128x64x16 (x8), P from smem (written swizzled by the softmax warps),
+//                        V as MN-major operand straight from its natural [key, d] layout
+// The running output O stays in TMEM; it is rescaled in place (tcgen05.ld/st) only when a row maximum grows.
+//
+// Epipolar mode: the reference materialises a bool mask [B, L, L] (268 MB per sample at 32x32x16) and
+// reads it in every layer.  Here the mask is evaluated inside the softmax pass from the 3x3 fundamental
+// matrices (9 floats per frame pair), with the reference's exact fp32 operation order
+// (R/model/camcontexti2v.py:229-239; FMA-chain contraction, separately rounded norm, IEEE sqrt/div),
+// so masked-out keys are bit-identical to the reference's mask and no mask ever touches HBM.
+#include "attn_tc.h"
+#include "common.cuh"
+
+namespace c2v {
+
+constexpr int AT_BM = 128;   // query rows per CTA
+constexpr int AT_BN = 128;   // keys per tile
+constexpr int AT_D = 64;
+constexpr int AT_KV_STAGES = 2;
+constexpr int AT_THREADS = 192;
+
+constexpr int AT_Q_BYTES = AT_BM * AT_D * 2;        // 16 KB
+constexpr int AT_K_BYTES = AT_BN * AT_D * 2;        // 16 KB
+constexpr int AT_V_BYTES = AT_BN * AT_D * 2;        // 16 KB
+constexpr int AT_P_BYTES = AT_BM * AT_BN * 2;       // 32 KB (two 64-key halves)
+constexpr int AT_OFF_Q = 0;
+constexpr int AT_OFF_K = AT_OFF_Q + AT_Q_BYTES;
+constexpr int AT_OFF_V = AT_OFF_K + AT_KV_STAGES * AT_K_BYTES;
+constexpr int AT_OFF_P = AT_OFF_V + AT_KV_STAGES * AT_V_BYTES;
+constexpr int AT_OFF_BAR = AT_OFF_P + AT_P_BYTES;
+constexpr int AT_SMEM = AT_OFF_BAR + 128;
+
+constexpr uint32_t AT_TMEM_COLS = 256;
+constexpr uint32_t AT_TM_S = 0;       // S accumulator: columns [0,128)
+constexpr uint32_t AT_TM_O = 128;     // O accumulator: columns [128,192)
+
+struct EpiLine {
+    float l0, l1, l2;
+};
+
+// Normalised epipolar line of query pixel (xi, yi) in frame t2 (camcontexti2v.py:229-236).
+__device__ __forceinline__ EpiLine epi_line(const float* __restrict__ f, float xi, float yi) {
+    float a0 = __fmaf_rn(f[2], 1.0f, __fmaf_rn(f[1], yi, __fmul_rn(f[0], xi)));
+    float a1 = __fmaf_rn(f[5], 1.0f, __fmaf_rn(f[4], yi, __fmul_rn(f[3], xi)));
+    float a2 = __fmaf_rn(f[8], 1.0f, __fmaf_rn(f[7], yi, __fmul_rn(f[6], xi)));
+    const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
+    EpiLine l;
+    l.l0 = __fdiv_rn(a0, nrm);
+    l.l1 = __fdiv_rn(a1, nrm);
+    l.l2 = __fdiv_rn(a2, nrm);
+    return l;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnKernelArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;    // [2]
+    uint64_t* kv_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_free = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* pv_done = bars + 8;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * AT_BM;
+    const int head = blockIdx.y;
+    const int b = blockIdx.z;
+    const int bkv = b / p.kv_div;
+    const int n_main = (p.lk + AT_BN - 1) / AT_BN;
+    const int n_tiles = n_main + (p.lk2 > 0 ? 1 : 0);       // last tile = register-token segment
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) {
+            printf("camc2v_b200: attention smem base not 1024B aligned\n");
+            __trap();
+        }
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        if (p.lk2 > 0) {
+            tma_prefetch_desc(&p.tmK2);
+            tma_prefetch_desc(&p.tmV2);
+        }
+        mbar_init(q_full, 1);
+        for (int s = 0; s < AT_KV_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 128);
+        mbar_init(p_full, 128);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, AT_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            mbar_expect_tx(q_full, AT_Q_BYTES);
+            tma_load_3d(smem + AT_OFF_Q, &p.tmQ, q_full, head * AT_D, q0, b);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % AT_KV_STAGES;
+                const uint32_t ph = (j / AT_KV_STAGES) & 1;
+                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_expect_tx(&kv_full[s], AT_K_BYTES + AT_V_BYTES);
+                if (j < n_main) {
+                    tma_load_3d(smem + AT_OFF_K + s * AT_K_BYTES, &p.tmK, &kv_full[s], head * AT_D, j * AT_BN, bkv);
+                    tma_load_3d(smem + AT_OFF_V + s * AT_V_BYTES, &p.tmV, &kv_full[s], head * AT_D, j * AT_BN, bkv);
+                } else {
+                    tma_load_3d(smem + AT_OFF_K + s * AT_K_BYTES, &p.tmK2, &kv_full[s], head * AT_D, 0, 0);
+                    tma_load_3d(smem + AT_OFF_V + s * AT_V_BYTES, &p.tmV2, &kv_full[s], head * AT_D, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, AT_D, 0, 1);   // B = V is MN-major
+        const uint32_t q_addr = smem_u32(smem + AT_OFF_Q);
+        const uint32_t p_addr = smem_u32(smem + AT_OFF_P);
+        auto issue_qk = [&](int j) {
+            const int s = j % AT_KV_STAGES;
+            mbar_wait(&kv_full[s], (j / AT_KV_STAGES) & 1);
+            if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t qd = umma_desc_sw128(q_addr);
+                const uint64_t kd = umma_desc_sw128(smem_u32(smem + AT_OFF_K + s * AT_K_BYTES));
+#pragma unroll
+                for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tmem_base + AT_TM_S, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+                umma_commit(s_full);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j % AT_KV_STAGES;
+            if (j + 1 < n_tiles) issue_qk(j + 1);     // overlaps with the softmax warps writing P(j)
+            mbar_wait(p_full, j & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t v_addr = smem_u32(smem + AT_OFF_V + s * AT_V_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < AT_BN / 16; ++ks) {
+                    const uint64_t pd = umma_desc_sw128(p_addr + (ks / 4) * (AT_BM * 128)) + 2 * (ks % 4);
+                    const uint64_t vd = umma_desc_sw128(v_addr + ks * 16 * 128);
+                    umma_bf16_ss(tmem_base + AT_TM_O, pd, vd, idesc_pv, (j | ks) != 0);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(pv_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax / correction / epilogue (warps 2..5) =====================
+        const int lg = warp & 3;
+        const int r = lg * 32 + lane_id();
+        const int qi = q0 + r;                                     // query index inside the batch
+        const uint32_t t_s = tmem_base + AT_TM_S + ((uint32_t)(lg * 32) << 16);
+        const uint32_t t_o = tmem_base + AT_TM_O + ((uint32_t)(lg * 32) << 16);
+        const bool epi = p.epi_F != nullptr;
+        const unsigned char* mrow = p.mask ? p.mask + (size_t)b * p.mask_bstride + (size_t)min(qi, p.lq - 1) * p.lk : nullptr;
+        // epipolar query geometry
+        const int HW = p.epi_H * p.epi_W;
+        float xi = 0.f, yi = 0.f;
+        const float* Frow = nullptr;
+        if (epi) {
+            const int qc = min(qi, p.lq - 1);
+            const int t1 = qc / HW, pix = qc % HW;
+            xi = __fadd_rn(__fmul_rn((float)(pix % p.epi_W), (float)p.epi_d), p.epi_off);
+            yi = __fadd_rn(__fmul_rn((float)(pix / p.epi_W), (float)p.epi_d), p.epi_off);
+            Frow = p.epi_F + ((size_t)b * p.epi_T + t1) * p.epi_T * 9;
+        }
+        int cur_t2 = -1;
+        EpiLine line = {0.f, 0.f, 0.f};
+
+        float m_run = -INFINITY;   // running max, already multiplied by scale*log2(e)
+        float l_run = 0.f;
+        uint8_t* p_row = smem + AT_OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
+
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t bits[4];
+            float mx = -INFINITY;
+            // ---- pass 1: validity mask + row max ----
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(t_s + c * 32, v);
+                tmem_ld_wait();
+                uint32_t bm = 0;
+                const bool main_seg = j < n_main;
+                const int key0 = (main_seg ? j * AT_BN : 0) + c * 32;
+                const int klim = main_seg ? p.lk : p.lk2;
+                uint32_t mw[8];
+                if (mrow && main_seg) {
+                    if (key0 + 32 <= p.lk && (p.lk & 15) == 0) {
+                        const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + key0);
+                        const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + key0 + 16);
+                        mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+                        mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+                    } else {
+#pragma unroll
+                        for (int w8 = 0; w8 < 8; ++w8) {
+                            uint32_t wv = 0;
+                            for (int e = 0; e < 4; ++e) {
+                                const int key = key0 + w8 * 4 + e;
+                                if (key < p.lk && mrow[key]) wv |= 1u << (8 * e);
+                            }
+                            mw[w8] = wv;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int key = key0 + i;
+                    bool ok = key < klim;
+                    if (mrow && main_seg) ok = ok && ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) != 0;
+                    if (epi && main_seg) {
+                        const int tok = key;
+                        const int t2 = tok / HW;
+                        if (t2 != cur_t2 && ok) {          // uniform across the warp (same key for every lane)
+                            cur_t2 = t2;
+                            line = epi_line(Frow + t2 * 9, xi, yi);
+                        }
+                        const int pj = tok - t2 * HW;
+                        const float xj = __fadd_rn(__fmul_rn((float)(pj % p.epi_W), (float)p.epi_d), p.epi_off);
+                        const float yj = __fadd_rn(__fmul_rn((float)(pj / p.epi_W), (float)p.epi_d), p.epi_off);
+                        const float dist = fabsf(__fmaf_rn(line.l2, 1.0f, __fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj))));
+                        ok = ok && (dist < p.epi_thr);
+                    }
+                    if (ok) {
+                        bm |= 1u << i;
+                        mx = fmaxf(mx, __uint_as_float(v[i]));
+                    }
+                }
+                bits[c] = bm;
+            }
+            const float m_new = fmaxf(m_run, mx * p.scale_log2);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
+            l_run *= alpha;
+            // ---- pass 2: probabilities ----
+            uint32_t pk[64];
+            float lsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(t_s + c * 32, v);
+                tmem_ld_wait();
+                const uint32_t bm = bits[c];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float e0 = (bm >> i) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use)) : 0.f;
+                    float e1 = (bm >> (i + 1)) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use)) : 0.f;
+                    // accumulate the row sum from the bf16-rounded values that the PV MMA will actually use
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+                    lsum += __low2float(h) + __high2float(h);
+                    pk[c * 16 + i / 2] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+            }
+            l_run += lsum;
+            m_run = m_new;
+            tc_fence_before();
+            mbar_arrive(s_free);                        // S(j) fully consumed: QK(j+1) may overwrite it
+            // ---- wait for PV(j-1): P buffer free, O stable ----
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(t_o + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(t_o + c * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // ---- write P (bf16) into the 128B-swizzled K-major layout expected by the PV MMA ----
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const int w = h * 32 + ch * 4;
+                    uint4 val = make_uint4(pk[w], pk[w + 1], pk[w + 2], pk[w + 3]);
+                    *reinterpret_cast<uint4*>(p_row + h * (AT_BM * 128) + ((ch ^ (r & 7)) << 4)) = val;
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l -> bf16 -> global ----
+        mbar_wait(pv_done, (n_tiles - 1) & 1);
+        tc_fence_after();
+        const float inv = (l_run > 0.f) ? p.out_scale / l_run : 0.f;
+        const bool row_ok = qi < p.lq;
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)b * p.o_bstride + (size_t)qi * p.ldo + head * AT_D;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_o + c * 32, o);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[i + e]) * inv;
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32 + i);
+                    if (p.accumulate) {
+                        const uint4 prev = *dst;
+                        const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            f[2 * e] += __low2float(ph[e]);
+                            f[2 * e + 1] += __high2float(ph[e]);
+                        }
+                    }
+                    *dst = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, AT_TMEM_COLS);
+    }
+}
+
+int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        C2V_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        attr_set = true;
+    }
+    attn_tc_kernel<<<dim3(q_tiles, heads, batch), AT_THREADS, AT_SMEM, st>>>(a);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+}  // namespace c2v

@@ -1,0 +1,30 @@
+// Kernel-side argument block of the tcgen05 flash attention (attn_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace c2v {
+
+struct AttnKernelArgs {
+    CUtensorMap tmQ, tmK, tmV;   // rank-3 bf16 maps (heads*64, rows, batch), box (64, 128, 1)
+    CUtensorMap tmK2, tmV2;      // optional extra key segment shared by all batches (epipolar register tokens)
+    int lk2;                     // rows of the extra segment (0 = none, <= 128)
+    void* out;                   // bf16
+    int lq, lk, kv_div;
+    int ldo;
+    long long o_bstride;
+    float scale_log2;            // 64^-0.5 * log2(e)
+    float out_scale;
+    int accumulate;
+    // epipolar mask over the main key segment: evaluated from F (null F and null mask => dense attention)
+    const float* epi_F;          // [B, T, T, 3, 3]
+    int epi_T, epi_H, epi_W, epi_d;
+    // alternatively a materialised mask in the reference's format: uint8/bool [B, lq, lk]
+    const unsigned char* mask;
+    long long mask_bstride;
+    float epi_thr, epi_off;      // float32(d*sqrt(2)/2), d/2 - 0.5
+};
+
+int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st);
+
+}  // namespace c2v

@@ -1,0 +1,313 @@
+// Layout changes, small glue ops and the fused CFG + DDIM update.  All HBM-bound: vectorised, coalesced,
+// one read and one write per element.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace c2v {
+
+static inline int grid_for(int64_t work, int threads, int cap = 148 * 16) {
+    int64_t g = (work + threads - 1) / threads;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// [B, C, S] fp32  <->  channels-last [B, S, Cpad]     (b c t h w <-> (b t) (h w) c of modified_forwards.py:48,130)
+// ------------------------------------------------------------------------------------------------
+template <bool OUT_BF16>
+__global__ void to_cl_kernel(const float* __restrict__ in, void* __restrict__ out, int C, int S, int Cpad) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, s = s0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && s < S) ? in[((size_t)b * C + c) * S + s] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int s = s0 + i, c = c0 + threadIdx.x;
+        if (s < S && c < Cpad) {
+            const float v = tile[threadIdx.x][i];
+            const size_t o = ((size_t)b * S + s) * Cpad + c;
+            if (OUT_BF16)
+                reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16(v);
+            else
+                reinterpret_cast<float*>(out)[o] = v;
+        }
+    }
+}
+
+__global__ void from_cl_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int S) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int s = s0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && s < S) ? in[((size_t)b * S + s) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, s = s0 + threadIdx.x;
+        if (c < C && s < S) out[((size_t)b * C + c) * S + s] = tile[threadIdx.x][i];
+    }
+}
+
+int to_channels_last_launch(const float* in, void* out, int B, int C, int S, int Cpad, int out_bf16, cudaStream_t st) {
+    if (Cpad < C || B <= 0 || B > 65535) return ERR_BAD_ARG;
+    dim3 grid((S + 31) / 32, (Cpad + 31) / 32, B), block(32, 8);
+    if (out_bf16)
+        to_cl_kernel<true><<<grid, block, 0, st>>>(in, out, C, S, Cpad);
+    else
+        to_cl_kernel<false><<<grid, block, 0, st>>>(in, out, C, S, Cpad);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+int from_channels_last_launch(const float* in, float* out, int B, int C, int S, cudaStream_t st) {
+    if (B <= 0 || B > 65535) return ERR_BAD_ARG;
+    dim3 grid((S + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    from_cl_kernel<<<grid, block, 0, st>>>(in, out, C, S);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel concat of the skip connection (modified_forwards.py:108), optional bf16 copy for the 1x1 skip conv
+// ------------------------------------------------------------------------------------------------
+__global__ void concat_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ of, __nv_bfloat16* __restrict__ ob,
+                              int64_t rows, int Ca, int Cb) {
+    const int nv = (Ca + Cb) >> 2, nva = Ca >> 2;
+    const int64_t total = rows * nv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / nv;
+        const int cv = (int)(i - r * nv);
+        const float4 v = cv < nva ? *reinterpret_cast<const float4*>(a + r * Ca + cv * 4)
+                                  : *reinterpret_cast<const float4*>(b + r * Cb + (cv - nva) * 4);
+        if (of) *reinterpret_cast<float4*>(of + i * 4) = v;
+        if (ob) *reinterpret_cast<uint2*>(ob + i * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+
+int concat_channels_launch(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, cudaStream_t st) {
+    if (Ca % 4 || Cb % 4) return ERR_UNSUPPORTED;
+    concat_kernel<<<grid_for(rows * ((Ca + Cb) >> 2), 256), 256, 0, st>>>(a, b, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, Ca, Cb);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n4, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = *reinterpret_cast<const float4*>(in + i * 4);
+        *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = n4 * 4; i < n; ++i) out[i] = __float2bfloat16(in[i]);
+}
+
+int cast_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t st) {
+    cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n / 4, n);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// nearest 2x upsample feeding the Upsample conv (openaimodel3d.py:101-105)
+__global__ void upsample2x_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+    const int nv = C >> 2;
+    const int64_t total = (int64_t)N * 4 * H * W * nv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % nv);
+        int64_t r = i / nv;
+        const int xo = (int)(r % (2 * W)); r /= 2 * W;
+        const int yo = (int)(r % (2 * H));
+        const int n = (int)(r / (2 * H));
+        const float4 v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + (yo >> 1)) * W + (xo >> 1)) * C + cv * 4);
+        *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+
+int upsample2x_launch(const float* in, void* out, int N, int H, int W, int C, cudaStream_t st) {
+    if (C % 4) return ERR_UNSUPPORTED;
+    upsample2x_kernel<<<grid_for((int64_t)N * 4 * H * W * (C >> 2), 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), N, H, W, C);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// im2col of the stride-2 Downsample conv (openaimodel3d.py:66-70): row (n, yo, xo), column tap*C + c
+__global__ void im2col_s2_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+    const int nv = C >> 2, Ho = H >> 1, Wo = W >> 1;
+    const int64_t total = (int64_t)N * Ho * Wo * 9 * nv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % nv);
+        int64_t r = i / nv;
+        const int tap = (int)(r % 9); r /= 9;
+        const int xo = (int)(r % Wo); r /= Wo;
+        const int yo = (int)(r % Ho);
+        const int n = (int)(r / Ho);
+        const int y = 2 * yo + tap / 3 - 1, x = 2 * xo + tap % 3 - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + y) * W + x) * C + cv * 4);
+        *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+
+int im2col_s2_launch(const float* in, void* out, int N, int H, int W, int C, cudaStream_t st) {
+    if (C % 4 || H % 2 || W % 2) return ERR_UNSUPPORTED;
+    im2col_s2_kernel<<<grid_for((int64_t)N * (H / 2) * (W / 2) * 9 * (C >> 2), 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), N, H, W, C);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+__global__ void copy_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int C, int64_t dst_bstride,
+                                 int ldd) {
+    const int b = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * C; i += gridDim.x * blockDim.x) {
+        const int r = i / C, c = i - r * C;
+        dst[(size_t)b * dst_bstride + (size_t)r * ldd + c] = src[i];
+    }
+}
+
+int copy_rows_launch(const void* src, void* dst, int rows, int C, int B, int64_t dst_bstride, int ldd, cudaStream_t st) {
+    copy_rows_kernel<<<dim3(grid_for((int64_t)rows * C, 256, 64), B), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+                                                                                  reinterpret_cast<__nv_bfloat16*>(dst), rows, C, dst_bstride, ldd);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small-M linear: one warp per output feature, weights streamed once (bf16, 16-byte loads)
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_MAXM = 8;
+__global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ out, int M, int N, int K,
+                                                            int silu_in) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    for (int m0 = 0; m0 < M; m0 += SK_MAXM) {
+        float acc[SK_MAXM];
+#pragma unroll
+        for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
+        for (int k = lane * 8; k < K; k += 256) {
+            const uint4 wv = *reinterpret_cast<const uint4*>(w + (size_t)n * K + k);
+            const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wv);
+            float wf[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                wf[2 * e] = __low2float(wh[e]);
+                wf[2 * e + 1] = __high2float(wh[e]);
+            }
+#pragma unroll
+            for (int m = 0; m < SK_MAXM; ++m) {
+                if (m0 + m < M) {
+                    const float* xr = in + (size_t)(m0 + m) * K + k;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float xv = xr[e];
+                        if (silu_in) xv = xv / (1.0f + expf(-xv));
+                        acc[m] = fmaf(xv, wf[e], acc[m]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < SK_MAXM; ++m) {
+            const float s = warp_sum(acc[m]);
+            if (lane == 0 && m0 + m < M) out[(size_t)(m0 + m) * N + n] = s + (bias ? bias[n] : 0.f);
+        }
+    }
+}
+
+int skinny_linear_launch(const float* in, const void* w, const float* bias, float* out, int M, int N, int K, int silu_in, cudaStream_t st) {
+    if (K % 8) return ERR_UNSUPPORTED;
+    skinny_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(in, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N, K, silu_in);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// sinusoidal embedding (utils_diffusion.py:8-28): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / half)
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int n, int dim) {
+    const int half = dim >> 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * half; i += gridDim.x * blockDim.x) {
+        const int r = i / half, c = i - r * half;
+        const float f = expf(__fdiv_rn(__fmul_rn(-9.210340371976184f, (float)c), (float)half));
+        const float a = __fmul_rn((float)t[r], f);
+        out[(size_t)r * dim + c] = cosf(a);
+        out[(size_t)r * dim + half + c] = sinf(a);
+    }
+}
+
+int timestep_embedding_launch(const int64_t* t, float* out, int n, int dim, cudaStream_t st) {
+    if (dim % 2) return ERR_UNSUPPORTED;
+    timestep_embedding_kernel<<<grid_for((int64_t)n * (dim / 2), 128, 64), 128, 0, st>>>(t, out, n, dim);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused CFG combine + guidance rescale + DDIM update (ddim.py:262-346, utils_diffusion.py:147-158).
+// One CTA per sample: the reference issues ~15 elementwise / reduction launches here.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (l == 0) sh[0] = t;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+__global__ void __launch_bounds__(1024) cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ ec, const float* __restrict__ eu,
+                                                        const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0,
+                                                        int64_t n, float scale, float phi, float a_t, float a_prev, float sigma_t,
+                                                        float sqrt_one_minus_at) {
+    __shared__ double sh[32];
+    const size_t base = (size_t)blockIdx.x * n;
+    x += base; ec += base; eu += base; noise += base; x_prev += base; pred_x0 += base;
+    float ratio = 1.f;
+    if (phi > 0.f) {
+        double sc = 0.0, se = 0.0;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const float c = ec[i], u = eu[i];
+            sc += c;
+            se += __fadd_rn(u, __fmul_rn(scale, __fsub_rn(c, u)));
+        }
+        const double mc = block_sum(sc, sh) / (double)n;
+        const double me = block_sum(se, sh) / (double)n;
+        double vc = 0.0, ve = 0.0;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const float c = ec[i], u = eu[i];
+            const float e = __fadd_rn(u, __fmul_rn(scale, __fsub_rn(c, u)));
+            vc += ((double)c - mc) * ((double)c - mc);
+            ve += ((double)e - me) * ((double)e - me);
+        }
+        vc = block_sum(vc, sh);
+        ve = block_sum(ve, sh);
+        ratio = (float)sqrt(vc / (double)(n - 1)) / (float)sqrt(ve / (double)(n - 1));
+    }
+    const float sqrt_at = sqrtf(a_t), sqrt_aprev = sqrtf(a_prev);
+    const float dir = sqrtf(fmaxf(1.0f - a_prev - sigma_t * sigma_t, 0.f));
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float c = ec[i], u = eu[i];
+        float e = __fadd_rn(u, __fmul_rn(scale, __fsub_rn(c, u)));
+        if (phi > 0.f) e = __fadd_rn(__fmul_rn(phi, __fmul_rn(e, ratio)), __fmul_rn(1.0f - phi, e));
+        const float p0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
+        pred_x0[i] = p0;
+        x_prev[i] = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0), __fmul_rn(dir, e)), __fmul_rn(sigma_t, noise[i]));
+    }
+}
+
+int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, const float* noise, float* x_prev, float* pred_x0, int B,
+                           int64_t n, float scale, float phi, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
+                           cudaStream_t st) {
+    if (B <= 0 || n <= 1) return ERR_BAD_ARG;
+    cfg_ddim_kernel<<<B, 1024, 0, st>>>(x, ec, eu, noise, x_prev, pred_x0, n, scale, phi, a_t, a_prev, sigma_t, sqrt_one_minus_at);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+}  // namespace c2v

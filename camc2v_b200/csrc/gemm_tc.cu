@@ -1,0 +1,274 @@
+// tcgen05 GEMM for every dense contraction of the UNet step that is not attention:
+//   * nn.Linear            (attention.py:58-62, 277, 301, 348, 378, 434, 451-455; epipolar.py:55-63; ...)
+//   * Conv2d 3x3 / 1x1     (openaimodel3d.py:151-155, 175-187, 68-70, 96, 386, 561-565)  as implicit GEMM
+//   * Conv3d (3,1,1)       (openaimodel3d.py:255-266)                                     as implicit GEMM
+//
+//   out[m, n] = sum_{tap, k} A[row(m) shifted by tap, k] * Wt[n, tap*Cin + k]  (+ bias[n] + rowbias[m / rows_per_group, n]
+//               + residual[m, n]);   optional GEGLU epilogue  out = x * gelu_erf(gate).
+//
+// Data layout: activations are channels-last bf16 ([rows, C]); A tiles are fetched by TMA straight from
+// the activation tensor — for convolutions a 4-D tensor map (C, W, H, N) / (C, HW, T, B) is sampled at
+// tap-shifted coordinates and TMA's out-of-bounds zero fill provides the padding, so no im2col buffer
+// ever exists in HBM.  Weights are [N, taps*Cin] bf16 (K-major).  Both operands land in 128B-swizzled
+// shared memory and feed tcgen05.mma (M=128, N=BN, K=16) with the fp32 accumulator in TMEM.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global).  3-stage smem ring, 2 CTAs per SM so that one
+// CTA's epilogue overlaps the other's main loop.
+#include "common.cuh"
+#include "gemm_tc.h"
+
+namespace c2v {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 3;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 128 + 1024;  // + barriers/tmem ptr + 1024B alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmKernelArgs p) {
+    using S = GemmSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int m_tile = blockIdx.x;
+    const int n0 = blockIdx.y * BN;
+    const int iters = p.taps * p.k_chunks;
+    constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            // first output row of this tile -> base coordinates of the A box
+            const int m0 = m_tile * p.tile_rows;
+            int c1 = 0, c2 = 0, c3 = 0;
+            if (p.a_mode == A_PLAIN) {
+                c1 = m0;
+            } else if (p.a_mode == A_CONV2D) {          // rows ordered (n, y, x)
+                const int hw = p.dim1 * p.dim2;
+                c3 = m0 / hw;
+                c2 = (m0 % hw) / p.dim1;
+                c1 = 0;
+            } else {                                    // A_CONVT: rows ordered (b, t, p)
+                const int thw = p.dim1 * p.dim2;
+                c3 = m0 / thw;
+                c2 = (m0 % thw) / p.dim1;
+                c1 = m0 % p.dim1;
+            }
+            const uint32_t tx = (uint32_t)p.tile_rows * BK * 2 + S::B_BYTES;
+            int it = 0;
+            for (int tap = 0; tap < p.taps; ++tap) {
+                int d1 = 0, d2 = 0;
+                if (p.a_mode == A_CONV2D) {
+                    d1 = tap % 3 - 1;
+                    d2 = tap / 3 - 1;
+                    if (p.taps == 1) d1 = d2 = 0;
+                } else if (p.a_mode == A_CONVT) {
+                    d2 = tap - 1;
+                    if (p.taps == 1) d2 = 0;
+                }
+                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + S::A_BYTES;
+                    mbar_expect_tx(&full_bar[s], tx);
+                    if (p.a_mode == A_PLAIN)
+                        tma_load_2d(a_dst, &p.tmA, &full_bar[s], kc * BK, c1);
+                    else
+                        tma_load_4d(a_dst, &p.tmA, &full_bar[s], kc * BK, c1 + d1, c2 + d2, c3);
+                    tma_load_2d(b_dst, &p.tmB, &full_bar[s], (tap * p.k_chunks + kc) * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + S::A_BYTES;
+                const uint64_t adesc = umma_desc_sw128(a_addr);
+                const uint64_t bdesc = umma_desc_sw128(b_addr);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
+                    umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);
+                if (it == iters - 1) umma_commit(acc_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int lg = warp & 3;                       // TMEM lane group this warp may access
+        const int r = lg * 32 + lane_id();             // row inside the tile
+        const int m = m_tile * p.tile_rows + r;
+        const bool row_ok = (r < p.tile_rows) && (m < p.M);
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
+        const float* rb = (p.rowbias && row_ok) ? p.rowbias + (size_t)(m / p.rows_per_group) * p.N : nullptr;
+        if (p.epi == EPI_GEGLU) {
+            constexpr int HALF = BN / 2;
+            const int no = blockIdx.y * HALF;          // output column base
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + no;
+#pragma unroll 1
+            for (int c = 0; c < HALF; c += 16) {
+                uint32_t xv[16], gv[16];
+                tmem_ld16(trow + c, xv);
+                tmem_ld16(trow + HALF + c, gv);
+                tmem_ld_wait();
+                if (row_ok) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
+                        float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
+                        if (p.bias) {
+                            x0 += p.bias[n0 + c + j];
+                            x1 += p.bias[n0 + c + j + 1];
+                            g0 += p.bias[n0 + HALF + c + j];
+                            g1 += p.bias[n0 + HALF + c + j + 1];
+                        }
+                        pk[j / 2] = pack_bf16(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(o + c);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + c, v);
+                tmem_ld_wait();
+                if (row_ok && n0 + c < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    const int nvalid = min(32, p.N - (n0 + c));
+                    if (nvalid == 32) {
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n0 + c + j);
+                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            }
+                        }
+                        if (rb) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(rb + n0 + c + j);
+                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            }
+                        }
+                        if (p.residual) {
+                            const float* rs = p.residual + (size_t)m * p.ldr + n0 + c;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(rs + j);
+                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            }
+                        }
+                        if (p.out_bf16) {
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n0 + c;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8)
+                                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                                              pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+                        } else {
+                            float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n0 + c;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                    } else {
+                        // ragged N tail (e.g. the 4-channel output conv): scalar path
+                        for (int j = 0; j < nvalid; ++j) {
+                            float x = f[j];
+                            const int n = n0 + c + j;
+                            if (p.bias) x += p.bias[n];
+                            if (rb) x += rb[n];
+                            if (p.residual) x += p.residual[(size_t)m * p.ldr + n];
+                            if (p.out_bf16)
+                                reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)m * p.ldo + n] = __float2bfloat16(x);
+                            else
+                                reinterpret_cast<float*>(p.out)[(size_t)m * p.ldo + n] = x;
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN>
+static int launch(const GemmKernelArgs& a, int m_tiles, int n_tiles, cudaStream_t st) {
+    using S = GemmSmem<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        C2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr_set = true;
+    }
+    gemm_tc_kernel<BN><<<dim3(m_tiles, n_tiles), GEMM_THREADS, S::TOTAL, st>>>(a);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+int gemm_tc_launch(const GemmKernelArgs& a, int bn, int m_tiles, int n_tiles, cudaStream_t st) {
+    switch (bn) {
+        case 64: return launch<64>(a, m_tiles, n_tiles, st);
+        case 128: return launch<128>(a, m_tiles, n_tiles, st);
+        case 160: return launch<160>(a, m_tiles, n_tiles, st);
+        case 256: return launch<256>(a, m_tiles, n_tiles, st);
+        default: return ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace c2v

@@ -1,0 +1,33 @@
+// Kernel-side argument block of the tcgen05 GEMM / implicit-GEMM convolution (gemm_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace c2v {
+
+enum AMode : int { A_PLAIN = 0, A_CONV2D = 1, A_CONVT = 2 };
+enum EpiMode : int { EPI_LINEAR = 0, EPI_GEGLU = 1 };
+
+struct GemmKernelArgs {
+    CUtensorMap tmA;        // activations (bf16): rank 2 [K, M] or rank 4 (C, W, H, N) / (C, HW, T, B)
+    CUtensorMap tmB;        // weights (bf16) [N, taps*Cin], K-major
+    int M, N;               // output rows / columns
+    int k_chunks;           // Cin / 64
+    int taps;               // 1, 3 (temporal conv) or 9 (3x3 conv)
+    int a_mode;             // AMode
+    int dim1, dim2;         // A_CONV2D: W, H    A_CONVT: HW, T
+    int tile_rows;          // valid rows per M tile (<= 128)
+    int epi;                // EpiMode
+    const float* bias;      // [N] or null
+    const float* rowbias;   // [M / rows_per_group, N] or null (timestep-embedding add of ResBlock)
+    int rows_per_group;
+    const float* residual;  // fp32 [M, ldr] or null
+    int ldr;
+    void* out;              // fp32 or bf16 [M, ldo]
+    int ldo;
+    int out_bf16;
+};
+
+int gemm_tc_launch(const GemmKernelArgs& a, int bn, int m_tiles, int n_tiles, cudaStream_t st);
+
+}  // namespace c2v

@@ -1,0 +1,232 @@
+// HBM-bound normalisation kernels on the channels-last fp32 residual stream.  Each writes the bf16
+// operand of the GEMM that follows, so norm + activation + cast is one read and one (half-size) write.
+//   GroupNorm(32) [+SiLU]: R/lvdm/basics.py:78-89 (GroupNormSpecific, fp32 statistics),
+//                          R/lvdm/modules/attention.py:273,343 (eps 1e-6),
+//                          R/lvdm/modules/networks/openaimodel3d.py:151-153,175-177,255-265 (eps 1e-5 + SiLU)
+//   LayerNorm:             R/lvdm/modules/attention.py:232-234
+#include "common.cuh"
+#include "kernels.h"
+
+namespace c2v {
+
+constexpr int GN_THREADS = 512;
+constexpr int GN_MAX_SLOTS = 2;   // C/4 <= GN_THREADS * GN_MAX_SLOTS  ->  C <= 4096
+
+// Thread mapping shared by both GroupNorm kernels: the C/4 float4 columns of a row are spread over the
+// threads (slot s handles column-vector tid%nvec + s*GN_THREADS when nvec > GN_THREADS); when a row is
+// narrower than the block several rows are processed side by side.  Every thread therefore owns a fixed
+// set of channels and every global access is a fully coalesced float4.
+struct GnMap {
+    int nvec, slots, rows_par, rsub, cv0;
+    bool active;
+};
+__device__ __forceinline__ GnMap gn_map(int C) {
+    GnMap m;
+    m.nvec = C >> 2;
+    if (m.nvec >= GN_THREADS) {
+        m.slots = (m.nvec + GN_THREADS - 1) / GN_THREADS;
+        m.rows_par = 1;
+        m.rsub = 0;
+        m.cv0 = threadIdx.x;
+        m.active = true;
+    } else {
+        m.slots = 1;
+        m.rows_par = GN_THREADS / m.nvec;
+        m.rsub = threadIdx.x / m.nvec;
+        m.cv0 = threadIdx.x % m.nvec;
+        m.active = m.rsub < m.rows_par;
+    }
+    return m;
+}
+
+// partial (sum, sumsq) per (sample, slab, group)
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws, int rows, int C,
+                                                              int rows_per_slab) {
+    __shared__ float s_sum[32], s_sq[32];
+    const int n = blockIdx.y, slab = blockIdx.x, nslab = gridDim.x;
+    if (threadIdx.x < 32) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0.f;
+    __syncthreads();
+    const GnMap m = gn_map(C);
+    const int cg = C / 32;
+    const int r0 = slab * rows_per_slab;
+    const int r1 = min(rows, r0 + rows_per_slab);
+    const float* xs = x + (size_t)n * rows * C;
+    if (m.active) {
+        for (int s = 0; s < m.slots; ++s) {
+            const int cv = m.cv0 + s * GN_THREADS;
+            if (cv >= m.nvec) break;
+            float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int r = r0 + m.rsub; r < r1; r += m.rows_par) {
+                const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)r * C + cv * 4);
+                a[0] += v.x; q[0] = fmaf(v.x, v.x, q[0]);
+                a[1] += v.y; q[1] = fmaf(v.y, v.y, q[1]);
+                a[2] += v.z; q[2] = fmaf(v.z, v.z, q[2]);
+                a[3] += v.w; q[3] = fmaf(v.w, v.w, q[3]);
+            }
+            const int g0 = (cv * 4) / cg, g3 = (cv * 4 + 3) / cg;
+            if (g0 == g3) {
+                atomicAdd(&s_sum[g0], a[0] + a[1] + a[2] + a[3]);
+                atomicAdd(&s_sq[g0], q[0] + q[1] + q[2] + q[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int g = (cv * 4 + e) / cg;
+                    atomicAdd(&s_sum[g], a[e]);
+                    atomicAdd(&s_sq[g], q[e]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float* w = ws + (((size_t)n * nslab + slab) * 32 + threadIdx.x) * 2;
+        w[0] = s_sum[threadIdx.x];
+        w[1] = s_sq[threadIdx.x];
+    }
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ ws,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              __nv_bfloat16* __restrict__ out, int rows, int C, int rows_per_slab,
+                                                              float eps, int silu) {
+    __shared__ float s_mean[32], s_rstd[32];
+    const int n = blockIdx.y, slab = blockIdx.x, nslab = gridDim.x;
+    if (threadIdx.x < 32) {
+        double s = 0.0, q = 0.0;
+        const float* w = ws + ((size_t)n * nslab * 32 + threadIdx.x) * 2;
+        for (int i = 0; i < nslab; ++i) {
+            s += (double)w[(size_t)i * 64];
+            q += (double)w[(size_t)i * 64 + 1];
+        }
+        const double cnt = (double)rows * (double)(C / 32);
+        const double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const GnMap m = gn_map(C);
+    if (!m.active) return;
+    const int cg = C / 32;
+    const int r0 = slab * rows_per_slab;
+    const int r1 = min(rows, r0 + rows_per_slab);
+    const float* xs = x + (size_t)n * rows * C;
+    __nv_bfloat16* os = out + (size_t)n * rows * C;
+    for (int s = 0; s < m.slots; ++s) {
+        const int cv = m.cv0 + s * GN_THREADS;
+        if (cv >= m.nvec) break;
+        float sc[4], sh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = cv * 4 + e;
+            const int g = c / cg;
+            sc[e] = s_rstd[g] * gamma[c];
+            sh[e] = beta[c] - s_mean[g] * sc[e];
+        }
+        for (int r = r0 + m.rsub; r < r1; r += m.rows_par) {
+            const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)r * C + cv * 4);
+            float y0 = fmaf(v.x, sc[0], sh[0]), y1 = fmaf(v.y, sc[1], sh[1]), y2 = fmaf(v.z, sc[2], sh[2]), y3 = fmaf(v.w, sc[3], sh[3]);
+            if (silu) {
+                y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3);
+            }
+            *reinterpret_cast<uint2*>(os + (size_t)r * C + cv * 4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+        }
+    }
+}
+
+static int gn_slabs(int ns, int rows, int* rows_per_slab) {
+    int target = 592 / (ns > 0 ? ns : 1);
+    if (target < 1) target = 1;
+    int slabs = (rows + 7) / 8;
+    if (slabs > target) slabs = target;
+    if (slabs < 1) slabs = 1;
+    *rows_per_slab = (rows + slabs - 1) / slabs;
+    return (rows + *rows_per_slab - 1) / *rows_per_slab;
+}
+
+int64_t groupnorm_ws_floats(int ns, int rows, int C) {
+    int rps;
+    const int slabs = gn_slabs(ns, rows, &rps);
+    return (int64_t)ns * slabs * 64;
+}
+
+int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps,
+                          int silu, cudaStream_t st) {
+    if (C % 32 != 0 || C % 4 != 0 || (C >> 2) > GN_THREADS * GN_MAX_SLOTS || ns <= 0 || rows <= 0) return ERR_UNSUPPORTED;
+    if (ns > 65535) return ERR_UNSUPPORTED;
+    int rps;
+    const int slabs = gn_slabs(ns, rows, &rps);
+    gn_stats_kernel<<<dim3(slabs, ns), GN_THREADS, 0, st>>>(x, ws, rows, C, rps);
+    gn_apply_kernel<<<dim3(slabs, ns), GN_THREADS, 0, st>>>(x, ws, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), rows, C, rps, eps, silu);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (two-pass mean / variance, fp32).
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 10;   // float4 per lane -> C <= 1280
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                        const float* __restrict__ add, __nv_bfloat16* __restrict__ out2, int rows, int C,
+                                                        float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nvec = C >> 2;
+    const float* xr = x + (size_t)row * C;
+    float4 v[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int cv = lane + i * 32;
+        if (cv < nvec) {
+            v[i] = *reinterpret_cast<const float4*>(xr + cv * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int cv = lane + i * 32;
+        if (cv < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int cv = lane + i * 32;
+        if (cv < nvec) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma + cv * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(beta + cv * 4);
+            const float y0 = (v[i].x - mean) * rstd * g.x + bb.x;
+            const float y1 = (v[i].y - mean) * rstd * g.y + bb.y;
+            const float y2 = (v[i].z - mean) * rstd * g.z + bb.z;
+            const float y3 = (v[i].w - mean) * rstd * g.w + bb.w;
+            *reinterpret_cast<uint2*>(out + (size_t)row * C + cv * 4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+            if (add) {
+                const float4 p = *reinterpret_cast<const float4*>(add + (size_t)row * C + cv * 4);
+                *reinterpret_cast<uint2*>(out2 + (size_t)row * C + cv * 4) =
+                    make_uint2(pack_bf16(y0 + p.x, y1 + p.y), pack_bf16(y2 + p.z, y3 + p.w));
+            }
+        }
+    }
+}
+
+int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, int rows, int C,
+                     float eps, cudaStream_t st) {
+    if (C % 4 != 0 || (C >> 2) > LN_MAXV * 32 || rows <= 0) return ERR_UNSUPPORTED;
+    if (add && !out2) return ERR_BAD_ARG;
+    const int wpb = 8;
+    layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), add,
+                                                                 reinterpret_cast<__nv_bfloat16*>(out2), rows, C, eps);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+}  // namespace c2v

@@ -1,0 +1,329 @@
+"""Kernel-level parity tests (GPU): every C-ABI entry point against a plain fp32 torch evaluation of the
+same operator on the same (bf16-rounded) inputs, and the integer/boolean kernels bit-exactly against oracle/.
+
+Tolerances: bf16 operands + fp32 accumulation.  For an output of bf16 dtype the bound is 2^-8 relative to the
+row scale (one bf16 rounding) plus accumulation noise; for fp32 outputs 2e-3 relative to max|ref| covers
+the fp32 accumulation-order difference of K <= 23k terms of bf16 products.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from camc2v_b200 import ops
+    return ops
+
+
+def rnd(*shape, seed=0, std=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * std).to(DEV).to(dtype)
+
+
+def close(out, ref, tol, what=""):
+    out, ref = out.float(), ref.float()
+    assert torch.isfinite(out).all(), f"{what}: non-finite output"
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    assert err <= tol * scale, f"{what}: max|err| {err:.4e} > {tol} * max|ref| {scale:.4e}"
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(256, 320, 320), (16384, 320, 320), (1000, 1280, 640), (77, 640, 1024), (4096, 512, 320),
+                                   (128, 4, 320), (300, 2560, 1280), (256, 1280, 5120)])
+def test_linear(M, N, K):
+    ops = _ops()
+    a = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    w = rnd(N, K, seed=2, std=K ** -0.5, dtype=torch.bfloat16)
+    bias = rnd(N, seed=3)
+    res = rnd(M, N, seed=4)
+    ref = a.float() @ w.float().t() + bias + res
+    out = ops.linear(a, w, bias=bias, residual=res)
+    close(out, ref, 2e-3, "linear fp32")
+    out16 = ops.linear(a, w, bias=bias, residual=res, out_dtype=torch.bfloat16)
+    close(out16, ref, 1e-2, "linear bf16")
+    # in-place residual (out aliases residual), as used for the attention / FF residual adds
+    res2 = res.clone()
+    ops.linear(a, w, bias=bias, residual=res2, out=res2)
+    close(res2, ref, 2e-3, "linear in-place")
+
+
+def test_linear_strided_a_and_rowbias():
+    ops = _ops()
+    M, K, N = 512, 320, 640
+    big = rnd(M, 3 * K, seed=5, dtype=torch.bfloat16)
+    a = big[:, K:2 * K]
+    w = rnd(N, K, seed=6, std=K ** -0.5, dtype=torch.bfloat16)
+    rb = rnd(4, N, seed=7)
+    ref = a.float() @ w.float().t() + rb.repeat_interleave(128, dim=0)
+    out = ops.linear(a, w, rowbias=rb, rows_per_group=128)
+    close(out, ref, 2e-3, "linear strided+rowbias")
+
+
+@pytest.mark.parametrize("C", [320, 512, 1280])
+def test_geglu(C):
+    ops = _ops()
+    M = 384
+    a = rnd(M, C, seed=1, dtype=torch.bfloat16)
+    w = rnd(8 * C, C, seed=2, std=C ** -0.5, dtype=torch.bfloat16)
+    b = rnd(8 * C, seed=3, std=0.1)
+    y = a.float() @ w.float().t() + b
+    x, gate = y.chunk(2, dim=-1)
+    ref = x * torch.nn.functional.gelu(gate)
+    w_il, b_il = ops.geglu_interleave(w, b)
+    out = ops.geglu_linear(a, w_il, b_il)
+    assert out.shape == (M, 4 * C)
+    close(out, ref, 1e-2, "geglu")
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(16, 32, 32, 64, 320), (16, 16, 16, 640, 640), (16, 8, 8, 1280, 1280), (16, 4, 4, 2560, 1280),
+                                             (2, 32, 32, 320, 4), (16, 2, 2, 256, 256), (32, 16, 16, 128, 128)])
+def test_conv3x3(NB, H, W, Cin, Cout):
+    ops = _ops()
+    x = rnd(NB, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, std=(9 * Cin) ** -0.5)
+    b = rnd(Cout, seed=3)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    ref = torch.nn.functional.conv2d(xb.float(), wb.float(), b, padding=1)
+    a = xb.permute(0, 2, 3, 1).reshape(NB * H * W, Cin).contiguous()
+    wk = wb.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    rb = rnd(NB // 2, Cout, seed=4)
+    res = rnd(NB * H * W, Cout, seed=5)
+    out = ops.conv3x3(a, wk, NB, H, W, bias=b, rowbias=rb, rows_per_group=2 * H * W, residual=res)
+    ref_cl = ref.permute(0, 2, 3, 1).reshape(NB * H * W, Cout) + rb.repeat_interleave(2 * H * W, dim=0) + res
+    close(out, ref_cl, 2e-3, "conv3x3")
+
+
+@pytest.mark.parametrize("B,T,HW,C", [(1, 16, 1024, 320), (2, 16, 256, 640), (1, 16, 64, 1280), (1, 16, 16, 1280), (1, 16, 4, 256)])
+def test_conv_t3(B, T, HW, C):
+    ops = _ops()
+    x = rnd(B, C, T, HW, 1, seed=1)
+    w = rnd(C, C, 3, 1, 1, seed=2, std=(3 * C) ** -0.5)
+    b = rnd(C, seed=3)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    ref = torch.nn.functional.conv3d(xb.float(), wb.float(), b, padding=(1, 0, 0))          # [B, C, T, HW, 1]
+    a = xb.squeeze(-1).permute(0, 2, 3, 1).reshape(B * T * HW, C).contiguous()
+    wk = wb.reshape(C, C, 3).permute(0, 2, 1).reshape(C, 3 * C).contiguous()
+    res = rnd(B * T * HW, C, seed=4)
+    out = ops.conv_t3(a, wk, B, T, HW, bias=b, residual=res)
+    ref_cl = ref.squeeze(-1).permute(0, 2, 3, 1).reshape(B * T * HW, C) + res
+    close(out, ref_cl, 2e-3, "conv_t3")
+
+
+def test_skinny_linear_and_timestep_embedding():
+    ops = _ops()
+    import sys
+    t = torch.tensor([999, 599, 39, 0], device=DEV)
+    emb = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    args = t.cpu()[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], dim=-1).to(DEV)
+    assert (emb - ref).abs().max().item() < 2e-4      # fp32 sin/cos of arguments up to 999 rad
+    x = rnd(4, 320, seed=1)
+    w = rnd(1280, 320, seed=2, std=320 ** -0.5, dtype=torch.bfloat16)
+    b = rnd(1280, seed=3)
+    close(ops.skinny_linear(x, w, b, False), x @ w.float().t() + b, 1e-5, "skinny")
+    close(ops.skinny_linear(x, w, b, True), torch.nn.functional.silu(x) @ w.float().t() + b, 1e-5, "skinny silu")
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("ns,rows,C,silu", [(16, 1024, 320, True), (1, 16384, 320, True), (16, 64, 1280, False), (16, 16, 2560, True),
+                                            (16, 256, 960, True), (2, 4096, 64, True), (16, 64, 1920, False)])
+def test_groupnorm(ns, rows, C, silu):
+    ops = _ops()
+    x = rnd(ns * rows, C, seed=1) * 3 + 0.5
+    g = rnd(C, seed=2) * 0.1 + 1
+    b = rnd(C, seed=3) * 0.1
+    ref = torch.nn.functional.group_norm(x.view(ns, rows, C).permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1).reshape(ns * rows, C)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    out = ops.groupnorm(x, g, b, ns, rows, 1e-5, silu)
+    close(out, ref, 6e-3, "groupnorm")
+
+
+@pytest.mark.parametrize("rows,C", [(16384, 320), (1000, 640), (256, 1280), (512, 512), (64, 64)])
+def test_layernorm(rows, C):
+    ops = _ops()
+    x = rnd(rows, C, seed=1) * 2 + 0.3
+    g = rnd(C, seed=2) * 0.1 + 1
+    b = rnd(C, seed=3) * 0.1
+    add = rnd(rows, C, seed=4) * 0.1
+    ref = torch.nn.functional.layer_norm(x, (C,), g, b, 1e-5)
+    out = ops.layernorm(x, g, b)
+    close(out, ref, 6e-3, "layernorm")
+    o1, o2 = ops.layernorm(x, g, b, add=add)
+    close(o1, ref, 6e-3, "layernorm.1")
+    close(o2, ref + add, 6e-3, "layernorm.2")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def ref_attention(q, k, v, heads, mask=None):
+    bq, lq, _ = q.shape
+    qh = q.float().view(bq, lq, heads, 64).permute(0, 2, 1, 3)
+    kh = k.float().view(k.shape[0], -1, heads, 64).permute(0, 2, 1, 3)
+    vh = v.float().view(v.shape[0], -1, heads, 64).permute(0, 2, 1, 3)
+    sim = qh @ kh.transpose(-1, -2) * 0.125
+    if mask is not None:
+        sim = sim.masked_fill(~mask[:, None], float("-inf"))
+    return (sim.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(bq, lq, heads * 64)
+
+
+@pytest.mark.parametrize("bq,lq,lk,heads,kv_div", [(16, 1024, 1024, 5, 1), (16, 256, 256, 10, 1), (16, 64, 64, 20, 1), (16, 16, 16, 20, 1),
+                                                   (16, 1024, 77, 5, 16), (16, 256, 768, 10, 16), (32, 64, 16, 20, 1), (2, 200, 333, 3, 1)])
+def test_attention_dense(bq, lq, lk, heads, kv_div):
+    ops = _ops()
+    C = heads * 64
+    bk = bq // kv_div
+    qkv = rnd(bq * lq, 3 * C, seed=1, dtype=torch.bfloat16)
+    q = qkv[:, :C]
+    if lq == lk and kv_div == 1:
+        k, v = qkv[:, C:2 * C], qkv[:, 2 * C:]
+    else:
+        kv = rnd(bk * lk, 2 * C, seed=2, dtype=torch.bfloat16)
+        k, v = kv[:, :C], kv[:, C:]
+    out = ops.attention(q, k, v, bq, lq, lk, heads, kv_div=kv_div)
+    kk = k.reshape(bk, lk, C).repeat_interleave(kv_div, dim=0)
+    vv = v.reshape(bk, lk, C).repeat_interleave(kv_div, dim=0)
+    ref = ref_attention(q.reshape(bq, lq, C), kk, vv, heads).reshape(bq * lq, C)
+    close(out, ref, 1.5e-2, "attention")
+    # accumulate: out += s * attention (image cross-attention sum)
+    out2 = ops.attention(q, k, v, bq, lq, lk, heads, kv_div=kv_div, out=out.clone(), out_scale=1.37, accumulate=True)
+    close(out2, ref * 2.37, 2e-2, "attention accumulate")
+
+
+@pytest.mark.parametrize("T,H,W,d,heads,kind", [(16, 8, 8, 32, 4, "pan_yaw"), (16, 4, 4, 64, 20, "orbit"), (16, 16, 16, 16, 2, "dolly"),
+                                                (16, 32, 32, 8, 1, "roll_pan_up")])
+def test_attention_epipolar(T, H, W, d, heads, kind):
+    """Mask evaluated in-kernel from F == attention with the oracle's materialised mask (+ register tokens)."""
+    import oracle
+    from oracle import camera_oracle
+    from camc2v_b200 import synth
+    ops = _ops()
+    K, w2c = synth.synth_camera(kind, T=T)
+    torch.manual_seed(123)
+    rel = camera_oracle.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))
+    Fm = camera_oracle.fundamental_matrices(K, rel)
+    mask = oracle.epipolar_mask(Fm, H, W, d).to(DEV)              # [1, L, L]
+    L, C, R = T * H * W, heads * 64, 4
+    qkv = rnd(L, 3 * C, seed=1, dtype=torch.bfloat16)
+    reg = rnd(R, 2 * C, seed=2, dtype=torch.bfloat16)
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    out = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm.to(DEV).contiguous(), epi_grid=(T, H, W), epi_d=d)
+    kk = torch.cat([reg[:, :C], k], 0)[None]
+    vv = torch.cat([reg[:, C:], v], 0)[None]
+    mm = torch.nn.functional.pad(mask, (R, 0), value=True)
+    ref = ref_attention(q[None], kk, vv, heads, mm)[0]
+    close(out, ref, 1.5e-2, "epipolar attention (F)")
+    # the same through the reference-format materialised mask
+    out_m = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], mask=mask.contiguous())
+    close(out_m, ref, 1.5e-2, "epipolar attention (mask)")
+    assert torch.equal(out, out_m), "F-evaluated and mask-driven attention must take identical decisions"
+
+
+@pytest.mark.parametrize("B,T,HW,heads", [(1, 16, 1024, 5), (2, 16, 64, 20), (1, 16, 256, 8), (1, 8, 16, 4)])
+def test_attention_temporal(B, T, HW, heads):
+    ops = _ops()
+    C = heads * 64
+    qkv = rnd(B * T * HW, 3 * C, seed=1, dtype=torch.bfloat16)
+    out = ops.attention_temporal(qkv, B, T, HW, heads)
+    x = qkv.view(B, T, HW, 3, C).permute(3, 0, 2, 1, 4).reshape(3, B * HW, T, C)
+    ref = ref_attention(x[0], x[1], x[2], heads).view(B, HW, T, C).permute(0, 2, 1, 3).reshape(B * T * HW, C)
+    close(out, ref, 1e-2, "temporal attention")
+
+
+# ------------------------------------------------------------------------------------------------ camera (bit-exact)
+@pytest.mark.parametrize("kind", ["pan_yaw", "stationary", "dolly", "yaw", "roll_pan_up", "orbit"])
+def test_epipolar_mask_bit_exact(kind):
+    import oracle
+    from oracle import camera_oracle
+    from camc2v_b200 import synth
+    ops = _ops()
+    K, w2c = synth.synth_camera(kind, T=16)
+    torch.manual_seed(123)
+    rel = camera_oracle.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))
+    Fm = camera_oracle.fundamental_matrices(K, rel)
+    gold = np.load("tests/golden/masks.npz")
+    assert np.array_equal(gold[f"{kind}.F"], Fm.numpy()), "F differs from the reference's (CPU torch build mismatch?)"
+    for d in (64, 32, 16, 8):
+        hw = 256 // d
+        got = ops.epipolar_mask(Fm.to(DEV), hw, hw, d).cpu()
+        if d >= 16:
+            want = oracle.epipolar_mask(Fm, hw, hw, d)
+            assert torch.equal(got, want), f"{kind} d={d}: {(got != want).sum().item()} mismatching mask bits"
+        packed = np.packbits(got.numpy(), axis=-1)
+        import hashlib
+        assert hashlib.sha256(packed.tobytes()).digest() == gold[f"{kind}.d{d}.sha256"].tobytes(), f"{kind} d={d}: sha256 mismatch vs reference"
+
+
+def test_plucker():
+    import oracle
+    from camc2v_b200 import synth
+    ops = _ops()
+    gold = np.load("tests/golden/masks.npz")
+    for kind in ("pan_yaw", "orbit"):
+        K, _ = synth.synth_camera(kind, T=16)
+        rel = torch.from_numpy(gold[f"{kind}.rel_c2w"])
+        for mode, key in (("plucker", "plucker_sub"), ("ray", "ray_sub")):
+            got = ops.plucker(K.to(DEV), rel.to(DEV), 256, 256, mode).cpu()
+            assert (got[..., 3::8, 3::8] - torch.from_numpy(gold[f"{kind}.{key}"])).abs().max().item() < 2e-6
+            assert (got - oracle.plucker(K, rel, 256, 256, mode)).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ glue
+def test_layout_and_glue():
+    ops = _ops()
+    B, Cc, T, H, W = 2, 8, 16, 32, 32
+    x = rnd(B, Cc, T, H, W, seed=1)
+    cl = ops.to_channels_last(x, B, Cc, T * H * W, Cpad=64, dtype=torch.bfloat16)
+    ref = torch.zeros(B * T * H * W, 64, device=DEV)
+    ref[:, :Cc] = x.permute(0, 2, 3, 4, 1).reshape(-1, Cc)
+    assert torch.equal(cl.float(), ref.to(torch.bfloat16).float())
+    y = rnd(B * T * H * W, 4, seed=2)
+    back = ops.from_channels_last(y, B, 4, T * H * W)
+    assert torch.equal(back.view(B, 4, T, H, W), y.view(B, T, H, W, 4).permute(0, 4, 1, 2, 3))
+    a, b = rnd(1000, 320, seed=3), rnd(1000, 640, seed=4)
+    of, ob = ops.concat_channels(a, b, True, True)
+    assert torch.equal(of, torch.cat([a, b], 1)) and torch.equal(ob, torch.cat([a, b], 1).to(torch.bfloat16))
+    assert torch.equal(ops.cast_bf16(a), a.to(torch.bfloat16))
+    img = rnd(4 * 8 * 8, 64, seed=5)
+    up = ops.upsample2x(img, 4, 8, 8)
+    ref_up = torch.nn.functional.interpolate(img.view(4, 8, 8, 64).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    assert torch.equal(up.view(4, 16, 16, 64), ref_up.permute(0, 2, 3, 1).to(torch.bfloat16))
+    col = ops.im2col_s2(img, 4, 8, 8)
+    unf = torch.nn.functional.unfold(img.view(4, 8, 8, 64).permute(0, 3, 1, 2), 3, padding=1, stride=2)   # [4, 64*9, 16]
+    ref_col = unf.view(4, 64, 9, 16).permute(0, 3, 2, 1).reshape(4 * 16, 9 * 64)
+    assert torch.equal(col, ref_col.to(torch.bfloat16))
+
+
+def test_downsample_conv_via_im2col():
+    ops = _ops()
+    NB, H, W, C = 16, 16, 16, 128
+    x = rnd(NB, C, H, W, seed=1).to(torch.bfloat16).float()
+    w = rnd(C, C, 3, 3, seed=2, std=(9 * C) ** -0.5).to(torch.bfloat16)
+    b = rnd(C, seed=3)
+    ref = torch.nn.functional.conv2d(x, w.float(), b, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, C)
+    col = ops.im2col_s2(x.permute(0, 2, 3, 1).reshape(-1, C).contiguous(), NB, H, W)
+    out = ops.linear(col, w.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous(), bias=b)
+    close(out, ref, 2e-3, "downsample conv")
+
+
+@pytest.mark.parametrize("phi", [0.0, 0.7])
+def test_cfg_ddim_update(phi):
+    from oracle import ddim_oracle
+    ops = _ops()
+    shape = (2, 4, 16, 32, 32)
+    x, ec, eu, nz = (rnd(*shape, seed=s) for s in (1, 2, 3, 4))
+    sch = ddim_oracle.ddim_schedule()
+    i = 14
+    args = (float(sch["alphas"][i]), float(sch["alphas_prev"][i]), float(sch["sigmas"][i]), float(sch["sqrt_one_minus_alphas"][i]))
+    xp, p0 = ops.cfg_ddim_update(x, ec, eu, nz, 3.5, phi, *args)
+    rxp, rp0 = ddim_oracle.cfg_ddim_update(x.cpu(), ec.cpu(), eu.cpu(), nz.cpu(), args[0], args[1], args[2], args[3], 3.5, phi)
+    assert (xp.cpu() - rxp).abs().max().item() < 2e-5 * rxp.abs().max().item()
+    assert (p0.cpu() - rp0).abs().max().item() < 2e-5 * rp0.abs().max().item()
