@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""Benchmark of the CamContextI2V denoising hot path on B200 (driver contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W     # CPU arm: the oracle port of the reference on host cores
+
+Workload (BASELINE.json configs[2]): 25-step DDIM sampling with classifier-free guidance 3.5, guidance
+rescale 0.7, eta 1, `uniform_trailing`, batch 1 video per GPU, 256x256x16f (4x32x32 latents), CamContextI2V
+UNet (1500.9 M params, random-init synthetic weights), 1 reference + 2 context frames (845-token cond context,
+333-token uncond context), synthetic pan+yaw camera trajectory.  A "step" is ONE DDIM step = cond UNet pass +
+uncond UNet pass + fused CFG/DDIM update.  metric = DDIM steps/s summed over GPUs (videos shard per GPU, no
+step-time collective; a final NCCL all_gather of the latents mirrors the north-star's latent gather).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from camc2v_b200 import synth  # noqa: E402
+from camc2v_b200.config import UNetConfig  # noqa: E402
+from camc2v_b200.flops import cfg_step_flops, unet_pass_flops  # noqa: E402
+from camc2v_b200.testing import synth_unet_inputs  # noqa: E402
+
+METRIC = "ddim_steps_per_s"
+UNIT = "DDIM steps/s (256x256, 16 frames, CFG)"
+CPU_SAMPLE_BLOCKS = {"input_blocks.0", "init_attn", "input_blocks.1", "input_blocks.2"}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.path = f"/tmp/c2v_clocks_{os.getpid()}.csv"
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def build_workload(cfg: UNetConfig, B: int, device, seed_offset: int = 0):
+    from camc2v_b200 import camera
+    from camc2v_b200.modules import build_unet
+    from camc2v_b200.sampler import DDIMSampler, DenoiserModel
+
+    unet = build_unet(cfg)
+    synth.fill_module_(unet, seed=0)
+    cpu_sd = None
+    model = DenoiserModel(unet).to(device)
+    sampler = DDIMSampler(model)
+    sampler.make_schedule(25, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
+    host = synth_unet_inputs(cfg, 32, 2, f"bench{seed_offset}", B=B)
+    K, w2c = synth.synth_camera("pan_yaw", T=cfg.temporal_length, B=B)
+    torch.manual_seed(123 + seed_offset)
+    cam_host = dict(K=K, w2c=w2c)
+    return model, sampler, host, cam_host, cpu_sd
+
+
+def to_device_conditioning(host, cam_host, device, static=None):
+    """Upload the once-per-video conditioning (pinned host -> device).  Returns (cond, uc, static, bytes)."""
+    from camc2v_b200 import camera
+    nbytes = 0
+    if static is None:
+        static = {}
+        for k in ("c_concat", "ctx_cond", "ctx_uncond"):
+            static[k] = torch.empty_like(host[k], device=device)
+        static["pluker"] = [torch.empty_like(p, device=device) for p in host["pluker"]]
+        static["fs"] = host["fs"].to(device)
+        B = host["x"].shape[0]
+        static["cam"] = camera.camera_condition(cam_host["K"], cam_host["w2c"], torch.zeros(B, dtype=torch.long), 256, 256,
+                                                pluker_embedding_features=static["pluker"], device=device)
+    for k in ("c_concat", "ctx_cond", "ctx_uncond"):
+        static[k].copy_(host[k], non_blocking=True)
+        nbytes += host[k].numel() * 4
+    for d, s in zip(static["pluker"], host["pluker"]):
+        d.copy_(s, non_blocking=True)
+        nbytes += s.numel() * 4
+    if nbytes and "cam" in static and static.get("_uploaded"):
+        # a new video: its poses arrive from the host and F is rebuilt (tiny 4x4 algebra) into the static buffer
+        rel = camera.relative_c2w(cam_host["w2c"], torch.zeros(cam_host["w2c"].shape[0], dtype=torch.long))
+        static["cam"]["epipolar_F"].copy_(camera.fundamental_matrices(cam_host["K"], rel), non_blocking=True)
+    static["_uploaded"] = True
+    nbytes += cam_host["K"].numel() * 4 + cam_host["w2c"].numel() * 4
+    cond = {"c_crossattn": [static["ctx_cond"]], "c_concat": [static["c_concat"]], "camera_condition": static["cam"]}
+    uc = {"c_crossattn": [static["ctx_uncond"]], "c_concat": [static["c_concat"]]}
+    return cond, uc, static, nbytes
+
+
+def pin(t):
+    try:
+        return t.pin_memory()
+    except Exception:
+        return t
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm / baseline
+def cpu_sample_setup(cfg: UNetConfig, full: bool = False):
+    """Oracle (CPU port of the reference) on a bounded sample of the workload: the first three input blocks +
+    init_attn of the cond pass at full size — 19.1 % of the cond pass, 10.0 % of a CFG step by algorithmic FLOPs."""
+    sys.path.insert(0, ROOT)
+    import oracle
+    from oracle import camera_oracle
+    from oracle.unet_oracle import UNetOracle
+    from camc2v_b200.config import build_topology
+    from camc2v_b200.modules import build_unet
+
+    topo = build_topology(cfg)
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in build_unet(cfg).state_dict().items()}
+    need = tuple(n + "." for n in ("input_blocks.0", "input_blocks.1", "input_blocks.2", "init_attn", "time_embed", "fps_embedding"))
+    sd = {k: synth.synth_param(k, s, 0) for k, s in shapes.items() if full or k.startswith(need)}
+    orc = UNetOracle(sd, cfg, fused_epipolar=True)
+    inp = synth_unet_inputs(cfg, 32, 2, "bench0", B=1)
+    K, w2c = synth.synth_camera("pan_yaw", T=cfg.temporal_length, B=1)
+    torch.manual_seed(123)
+    Fm, masks, _ = camera_oracle.camera_condition_masks(K, w2c, torch.zeros(1, dtype=torch.long), resolutions=(8, 4, 2, 1) if full else (1,))
+    cam = {"pluker_embedding_features": inp["pluker"], "sample_locs_dict": masks, "add_type": "add_to_main_branch"}
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    t = torch.full((1,), 599, dtype=torch.long)
+    blocks = None if full else CPU_SAMPLE_BLOCKS
+    frac = (unet_pass_flops(cfg, 1, 32, 845, False, only_blocks=blocks)["total"] / cfg_step_flops(cfg, 1, 32))
+
+    def run():
+        t0 = time.perf_counter()
+        orc.forward(xc, t, inp["ctx_cond"], inp["fs"], cam, max_input_block=None if full else 2)
+        return time.perf_counter() - t0
+
+    return run, frac
+
+
+def cpu_baseline(cfg: UNetConfig, repeats: int = 1):
+    torch.set_num_threads(os.cpu_count() or 1)
+    run, frac = cpu_sample_setup(cfg)
+    run()                                   # warm-up (allocator, oneDNN primitive caches)
+    best = min(run() for _ in range(max(1, repeats)))
+    what = "input_blocks.0-2 + init_attn of the cond UNet pass"
+    if best * 5.3 < 25.0:                   # fast host: afford the whole cond pass (52.5 % of a step) as the sample
+        run, frac = cpu_sample_setup(cfg, full=True)
+        best = run()
+        what = "the whole cond UNet pass"
+    return {"value": frac / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle (CPU port of the reference, fp32) on {what} at full size "
+                      f"(B=1, 4x16x32x32 latent, 845-token context, epipolar masks) = {frac * 100:.2f}% of one CFG step's algorithmic "
+                      f"FLOPs; {best:.2f} s per sample, steps/s extrapolated by FLOP share (the unmodified reference measured "
+                      f"57.3 s per full CFG step on 8 cores, BASELINE.md)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = UNetConfig()
+    torch.set_num_threads(os.cpu_count() or 1)
+    run, frac = cpu_sample_setup(cfg)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    el = time.perf_counter() - t0
+    per = el / args.steps
+    value = frac / per
+    base = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"per step: oracle (CPU port of the reference, fp32, all host threads) on input_blocks.0-2 + init_attn of the cond pass "
+                      f"at full size = {frac * 100:.2f}% of one CFG step's algorithmic FLOPs; steps/s extrapolated by FLOP share"}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per / frac * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(1, args.gpus), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(B, n_gpus):
+    return {"workload": "CamContextI2V 25-step DDIM sampling, CFG 3.5, guidance_rescale 0.7, eta 1, uniform_trailing, 256x256x16f "
+                        "(BASELINE.json configs[2]); one step = cond + uncond UNet pass + fused CFG/DDIM update",
+            "videos_per_gpu": B, "global_batch": B * n_gpus, "latent": [4, 16, 32, 32], "unet_params_m": 1500.9,
+            "context_tokens": {"cond": 845, "uncond": 333}, "ddim_steps_per_video": 25, "parallelism": f"dp{n_gpus} (videos sharded per GPU)",
+            "l2": "inputs larger than L2: 3.0 GB of bf16 weights are streamed every UNet pass (L2 = 126 MB)"}
+
+
+# ------------------------------------------------------------------------------------------------ dominant kernel
+def time_dominant_kernel(device, peaks):
+    """Epipolar-masked attention at the 32x32 level (L = 16384, 5 heads): the single largest kernel of the step
+    (1.72 of 7.87 TFLOP per pass).  Timed alone, CUDA events on the launching stream, L2 flushed between launches."""
+    from camc2v_b200 import camera, ops
+    T, H, W, heads, d = 16, 32, 32, 5, 8
+    L, C = T * H * W, heads * 64
+    g = torch.Generator(device="cpu").manual_seed(0)
+    qkv = torch.randn(L, 3 * C, generator=g).to(device).to(torch.bfloat16)
+    reg = torch.randn(4, 2 * C, generator=g).to(device).to(torch.bfloat16)
+    K, w2c = synth.synth_camera("pan_yaw", T=T)
+    torch.manual_seed(123)
+    Fm = camera.fundamental_matrices(K, camera.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))).to(device).contiguous()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def launch():
+        return ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm,
+                             epi_grid=(T, H, W), epi_d=d)
+
+    for _ in range(3):
+        launch()
+    times = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    flops = 4.0 * L * (L + 4) * C
+    achieved = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "attn_epipolar_L0_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    peak = peaks[0]["bf16_tflops"]
+    return {"bound": "tensor", "kernel": "attn_tc_kernel (epipolar-masked attention, L=16384, 5 heads, d=64; mask evaluated in-kernel)",
+            "achieved": achieved, "peak": peak, "peak_source": f"{peaks[1]} burst bf16 (kernel timed alone)", "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": traffic, "ms_per_launch": ms, "flops_per_launch": flops}
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=25)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=1, help="videos per GPU")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(3, args.warmup)
+
+    import torch.distributed as dist
+    from camc2v_b200 import _lib, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the camc2v_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+    peaks = measured_peaks()
+    cfg = UNetConfig()
+    B = args.batch
+    model, sampler, host, cam_host, _ = build_workload(cfg, B, device, seed_offset=rank)
+    for k in ("x", "c_concat", "ctx_cond", "ctx_uncond"):
+        host[k] = pin(host[k])
+    host["pluker"] = [pin(p) for p in host["pluker"]]
+    cond, uc, static, cond_bytes = to_device_conditioning(host, cam_host, device)
+    kw = dict(unconditional_guidance_scale=3.5, unconditional_conditioning=uc, guidance_rescale=0.7, fs=static["fs"],
+              enable_camera_condition=True, use_cuda_graph=not args.no_graph)
+    steps_per_video = 25
+    ts_table = np.flip(sampler.ddim_timesteps).copy()
+
+    def ddim_step(x, i):
+        index = steps_per_video - 1 - (i % steps_per_video)
+        ts = torch.full((B,), int(ts_table[i % steps_per_video]), device=device, dtype=torch.long)
+        x_prev, _ = sampler.p_sample_ddim(x, cond, ts, index=index, **kw)
+        return x_prev
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (`value`) ----------------
+    x = host["x"].to(device)
+    for i in range(args.warmup):
+        x = ddim_step(x, i)
+    barrier()
+    launches0 = _lib.LAUNCHES
+    graph_kernels = 0
+    if not args.no_graph and sampler._graph is not None:
+        # kernels inside the captured graph are replayed once per step
+        n0 = _lib.LAUNCHES
+        model.apply_model(sampler._graph["x"], sampler._graph["t"], cond, fs=static["fs"], enable_camera_condition=True)
+        model.apply_model(sampler._graph["x"], sampler._graph["t"], uc, fs=static["fs"], enable_camera_condition=True)
+        graph_kernels = _lib.LAUNCHES - n0
+        barrier()
+        launches0 = _lib.LAUNCHES
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    x = host["x"].to(device)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        x = ddim_step(x, i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    eager_kernels = _lib.LAUNCHES - launches0
+    gpu_launches = eager_kernels + graph_kernels * args.steps
+    tms = torch.tensor([ms], device=device)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = args.steps * B * world / (ms * 1e-3)  # video-steps per second: one step advances B videos per GPU by one DDIM step
+    finite = bool(torch.isfinite(x).all())
+
+    # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
+    x_host = pin(host["x"].clone())
+    out_host = pin(torch.empty_like(host["x"]))
+    x_dev = torch.empty_like(x)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for i in range(args.steps):
+        if i % steps_per_video == 0:             # a new video: its conditioning is uploaded once (as get_batch_input would produce it once)
+            _, _, _, nb = to_device_conditioning(host, cam_host, device, static)
+            h2d += nb
+        x_dev.copy_(x_host, non_blocking=True)
+        h2d += x_host.numel() * 4 + B * 8
+        xp = ddim_step(x_dev, i)
+        out_host.copy_(xp, non_blocking=True)
+        d2h += xp.numel() * 4
+        torch.cuda.current_stream().synchronize()          # the caller consumes x_prev on the host every step
+        x_host, out_host = out_host, x_host
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = args.steps * B * world / float(te.item())
+
+    # the north star's only collective: gather the final latents over NVLink
+    if world > 1:
+        gathered = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(gathered, x)
+
+    if rank == 0:
+        step_flops = cfg_step_flops(cfg, B, 32)
+        sustained = peaks[0].get("bf16_tflops_sustained", peaks[0]["bf16_tflops"])
+        per_gpu_tflops = step_flops * (value / world) / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(B, world),
+                "videos_per_s": value / steps_per_video,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+                "gpu_launches": int(gpu_launches), "clocks": clk, "finite": finite,
+                "step_roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": sustained, "unit": "TFLOP/s",
+                                  "frac": per_gpu_tflops / sustained, "flops_per_step": step_flops,
+                                  "peak_source": f"{peaks[1]} sustained bf16 (whole step)"}}
+        try:
+            line["roofline"] = time_dominant_kernel(device, peaks)
+        except Exception as e:  # the bench line must still be printed
+            line["roofline"] = {"error": repr(e)}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(cfg)
+            except Exception as e:
+                line["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,209 @@
+"""DDIM / classifier-free-guidance sampling loop on the CUDA path.
+
+Mirrors the sampler <-> model contract of the reference:
+    DDIMSampler.make_schedule / sample / ddim_sampling / p_sample_ddim   R/lvdm/models/samplers/ddim.py:24-346
+    LatentDiffusion.apply_model + DiffusionWrapper.forward ('hybrid')     R/lvdm/models/ddpm3d.py:724-739, 1268-1272
+    DDPM.register_schedule (linear betas)                                 R/lvdm/models/ddpm3d.py:125-188
+The sampler works with any object that honours that contract (`apply_model`, `alphas_cumprod`, `betas`,
+`num_timesteps`, `parameterization`, `use_dynamic_rescale`, `device`) — e.g. the reference's own
+LightningModule whose UNet has been swapped for camc2v_b200.modules.UNetModel — or with
+the light `DenoiserModel` below.
+
+What changes versus the reference: the ~15 elementwise / reduction launches of the CFG combine, guidance
+rescale and DDIM update are ONE kernel (ops.cfg_ddim_update); the schedule scalars stay on the host (no
+`.item()`-style device syncs per step); the camera condition is not deep-copied every step (ddim.py:259);
+and the two UNet passes of a step can be replayed from a CUDA graph (`use_cuda_graph=True`).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import UNetModel
+
+
+def make_beta_schedule_linear(n_timestep=1000, linear_start=0.00085, linear_end=0.012) -> np.ndarray:
+    return (np.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=np.float64) ** 2)
+
+
+def make_ddim_timesteps(method: str, n_ddim: int, n_ddpm: int) -> np.ndarray:
+    if method == "uniform":
+        c = n_ddpm // n_ddim
+        return np.asarray(list(range(0, n_ddpm, c))) + 1
+    if method == "uniform_trailing":
+        c = n_ddpm / n_ddim
+        return np.flip(np.round(np.arange(n_ddpm, 0, -c))).astype(np.int64) - 1
+    if method == "quad":
+        return ((np.linspace(0, np.sqrt(n_ddpm * .8), n_ddim)) ** 2).astype(int) + 1
+    raise NotImplementedError(f'There is no ddim discretization method called "{method}"')
+
+
+class DiffusionWrapper(nn.Module):
+    """ddpm3d.py:1251-1318, conditioning_key == 'hybrid' (the DynamiCrafter / CamContextI2V setting)."""
+
+    def __init__(self, diffusion_model: UNetModel, conditioning_key: str = "hybrid"):
+        super().__init__()
+        assert conditioning_key == "hybrid"
+        self.diffusion_model = diffusion_model
+        self.conditioning_key = conditioning_key
+
+    def forward(self, x, t, c_concat: list = None, c_crossattn: list = None, **kwargs):
+        xc = torch.cat([x] + c_concat, dim=1)
+        cc = torch.cat(c_crossattn, 1)
+        return self.diffusion_model(xc, t, context=cc, **kwargs)
+
+
+class DenoiserModel(nn.Module):
+    """The part of LatentDiffusion the sampler touches: schedule buffers + apply_model (ddpm3d.py:125-188, 724-739)."""
+
+    def __init__(self, unet: UNetModel, timesteps=1000, linear_start=0.00085, linear_end=0.012, parameterization="eps"):
+        super().__init__()
+        assert parameterization == "eps"
+        self.model = DiffusionWrapper(unet)
+        self.parameterization = parameterization
+        self.use_dynamic_rescale = False
+        self.num_timesteps = timesteps
+        betas = make_beta_schedule_linear(timesteps, linear_start, linear_end)
+        ac = np.cumprod(1.0 - betas, axis=0)
+        self.register_buffer("betas", torch.tensor(betas, dtype=torch.float32))
+        self.register_buffer("alphas_cumprod", torch.tensor(ac, dtype=torch.float32))
+        self.register_buffer("alphas_cumprod_prev", torch.tensor(np.append(1.0, ac[:-1]), dtype=torch.float32))
+
+    @property
+    def device(self):
+        return self.betas.device
+
+    def apply_model(self, x_noisy, t, cond, **kwargs):
+        if not isinstance(cond, dict):
+            raise NotImplementedError("hybrid conditioning expects a dict with c_concat / c_crossattn")
+        out = self.model(x_noisy, t, **cond, **kwargs)
+        return out[0] if isinstance(out, tuple) else out
+
+
+class DDIMSampler(object):
+    def __init__(self, model, schedule="linear", **kwargs):
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+        self._graph = None
+
+    # -------------------------------------------------------------------------------------------- schedule
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
+        """ddim.py:24-57; all per-step coefficients are kept as host fp32 numpy arrays."""
+        self.ddim_timesteps = make_ddim_timesteps(ddim_discretize, ddim_num_steps, self.ddpm_num_timesteps)
+        ac = self.model.alphas_cumprod.detach().float().cpu()
+        assert ac.shape[0] == self.ddpm_num_timesteps, 'alphas have to be defined for each timestep'
+        if getattr(self.model, "use_dynamic_rescale", False):
+            raise NotImplementedError("use_dynamic_rescale")
+        acn = ac.numpy()
+        a = acn[self.ddim_timesteps].astype(np.float64)
+        a_prev = np.asarray([acn[0]] + acn[self.ddim_timesteps[:-1]].tolist(), dtype=np.float64)
+        sig = ddim_eta * np.sqrt((1 - a_prev) / (1 - a) * (1 - a / a_prev))
+        self.ddim_alphas = a.astype(np.float32)
+        self.ddim_alphas_prev = a_prev.astype(np.float32)
+        self.ddim_sigmas = sig.astype(np.float32)
+        self.ddim_sqrt_one_minus_alphas = np.sqrt(1. - a).astype(np.float32)
+
+    # -------------------------------------------------------------------------------------------- sampling
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, eta=0., temperature=1., verbose=False, x_T=None,
+               unconditional_guidance_scale=1., unconditional_conditioning=None, fs=None, timestep_spacing='uniform',
+               guidance_rescale=0.0, use_cuda_graph=False, **kwargs):
+        self.make_schedule(ddim_num_steps=S, ddim_discretize=timestep_spacing, ddim_eta=eta, verbose=False)
+        if len(shape) == 3:
+            size = (batch_size,) + tuple(shape)
+        else:
+            size = (batch_size,) + tuple(shape)
+        return self.ddim_sampling(conditioning, size, x_T=x_T, temperature=temperature,
+                                  unconditional_guidance_scale=unconditional_guidance_scale,
+                                  unconditional_conditioning=unconditional_conditioning, fs=fs,
+                                  guidance_rescale=guidance_rescale, use_cuda_graph=use_cuda_graph, **kwargs)
+
+    @torch.no_grad()
+    def ddim_sampling(self, cond, shape, x_T=None, temperature=1., unconditional_guidance_scale=1.,
+                      unconditional_conditioning=None, fs=None, guidance_rescale=0.0, log_every_t=100, use_cuda_graph=False,
+                      img_callback=None, **kwargs):
+        """ddim.py:134-238 (the mask / paste / noise-shaping editing branches are outside the per-step scope)."""
+        device = self.model.betas.device
+        b = shape[0]
+        img = torch.randn(shape, device=device) if x_T is None else x_T
+        timesteps = self.ddim_timesteps
+        intermediates = {'x_inter': [img], 'pred_x0': [img]}
+        total_steps = timesteps.shape[0]
+        for i, step in enumerate(np.flip(timesteps)):
+            index = total_steps - i - 1
+            ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, temperature=temperature,
+                                              unconditional_guidance_scale=unconditional_guidance_scale,
+                                              unconditional_conditioning=unconditional_conditioning, fs=fs,
+                                              guidance_rescale=guidance_rescale, use_cuda_graph=use_cuda_graph, **kwargs)
+            if img_callback:
+                img_callback(pred_x0, i)
+            if index % log_every_t == 0 or index == total_steps - 1:
+                intermediates['x_inter'].append(img)
+                intermediates['pred_x0'].append(pred_x0)
+        return img, intermediates
+
+    # -------------------------------------------------------------------------------------------- one step
+    def _unet_pair(self, x, t, c, uc, kwargs, use_cuda_graph):
+        """The two apply_model calls of a CFG step (ddim.py:262-263), optionally replayed from one CUDA graph."""
+        if not use_cuda_graph:
+            return self.model.apply_model(x, t, c, **kwargs), self.model.apply_model(x, t, uc, **kwargs)
+        g = self._graph
+        key = (id(c), id(uc), tuple(x.shape))
+        if g is None or g["key"] != key:
+            sx, st = x.clone(), t.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up outside capture: builds weight packs, fills allocator pools
+                self.model.apply_model(sx, st, c, **kwargs)
+                self.model.apply_model(sx, st, uc, **kwargs)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                ec = self.model.apply_model(sx, st, c, **kwargs)
+                eu = self.model.apply_model(sx, st, uc, **kwargs)
+            g = self._graph = dict(key=key, graph=graph, x=sx, t=st, ec=ec, eu=eu)
+        g["x"].copy_(x)
+        g["t"].copy_(t)
+        g["graph"].replay()
+        return g["ec"], g["eu"]
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
+                      temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1., unconditional_conditioning=None, uc_type=None,
+                      conditional_guidance_scale_temporal=None, mask=None, x0=None, guidance_rescale=0.0, noise=None,
+                      use_cuda_graph=False, **kwargs):
+        """ddim.py:241-346.  `noise` (optional) lets a caller supply the eta-noise; otherwise torch.randn is drawn at
+        the same point of the RNG stream as the reference (ddim.py:340)."""
+        if use_original_steps or quantize_denoised or score_corrector is not None or noise_dropout > 0. or repeat_noise:
+            raise NotImplementedError("option outside the CamContextI2V sampling protocol")
+        a_t = float(self.ddim_alphas[index])
+        a_prev = float(self.ddim_alphas_prev[index])
+        sigma_t = float(self.ddim_sigmas[index])
+        s1m = float(self.ddim_sqrt_one_minus_alphas[index])
+        camera_cfg = kwargs.get("camera_cfg", 1.0)
+        if camera_cfg != 1.0:
+            raise NotImplementedError("camera_cfg != 1.0 (third UNet pass, ddim.py:268-280)")
+        if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
+            e_c = self.model.apply_model(x, t, c, **kwargs)
+            e_u, scale, phi = e_c, 1.0, 0.0
+        else:
+            uc = unconditional_conditioning
+            if kwargs.get("enable_camera_condition", False) and isinstance(c, dict):
+                # the reference deep-copies the masks into uc every step (ddim.py:259-260); sharing the dict is equivalent
+                cam = c.get("camera_condition")
+                if cam is not None and uc.get("camera_condition") is not cam:
+                    uc["camera_condition"] = cam
+            e_c, e_u = self._unet_pair(x, t, c, uc, kwargs, use_cuda_graph)
+            scale, phi = float(unconditional_guidance_scale), float(guidance_rescale)
+        if noise is None:
+            noise = torch.randn(x.shape, device=x.device)
+        if temperature != 1.:
+            noise = noise * temperature
+        return ops.cfg_ddim_update(x.float(), e_c, e_u, noise, scale, phi, a_t, a_prev, sigma_t, s1m)
