@@ -58,7 +58,11 @@ __device__ __forceinline__ EpiLine epi_line(const float* __restrict__ f, float x
     return l;
 }
 
+// LOGW >= 3 selects the fast epipolar predicate for square 2^LOGW x 2^LOGW key grids with pixel pitch D
+// (LOGW = 0: dense attention, materialised masks and arbitrary grids).
+template <int LOGW, int D>
 __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnKernelArgs p) {
+    constexpr bool FAST = LOGW >= 3;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
     uint64_t* q_full = bars + 0;
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         }
         int cur_t2 = -1;
         EpiLine line = {0.f, 0.f, 0.f};
+        float thr_m = 0.f;         // threshold + rounding margin for the conservative row test (fast path)
 
         float m_run = -INFINITY;   // running max, already multiplied by scale*log2(e)
         float l_run = 0.f;
@@ -200,60 +205,117 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             uint32_t bits[4];
+            uint32_t anyc = 0;       // chunks in which at least one lane of this warp has a valid key (warp-uniform)
             float mx = -INFINITY;
+            const bool main_seg = j < n_main;
+            const int klim = main_seg ? p.lk : p.lk2;
+            const int tile_key0 = main_seg ? j * AT_BN : 0;
             // ---- pass 1: validity mask + row max ----
+            if (FAST && epi && main_seg) {
+                // Square power-of-two key grid: a 32-key chunk is RPC whole image rows of one frame, pixel x of column i
+                // is a compile-time constant and the reference's mask predicate costs FMUL+FFMA+FADD+FSETP per element.
+                constexpr int W = 1 << (FAST ? LOGW : 5);
+                constexpr int RPC = 32 / W;
+                constexpr float DF = (float)D, OFFC = (float)D * 0.5f - 0.5f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(t_s + c * 32, v);
-                tmem_ld_wait();
-                uint32_t bm = 0;
-                const bool main_seg = j < n_main;
-                const int key0 = (main_seg ? j * AT_BN : 0) + c * 32;
-                const int klim = main_seg ? p.lk : p.lk2;
-                uint32_t mw[8];
-                if (mrow && main_seg) {
-                    if (key0 + 32 <= p.lk && (p.lk & 15) == 0) {
-                        const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + key0);
-                        const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + key0 + 16);
-                        mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
-                        mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
-                    } else {
+                for (int c = 0; c < 4; ++c) {
+                    const int key0 = tile_key0 + c * 32;
+                    const int t2 = key0 >> (2 * LOGW);
+                    if (t2 != cur_t2) {                     // warp-uniform: once per key frame
+                        cur_t2 = t2;
+                        line = epi_line(Frow + t2 * 9, xi, yi);
+                        const float cmax = (float)(W - 1) * DF + OFFC;
+                        thr_m = p.epi_thr + 1e-6f + 4e-7f * (fabsf(line.l0) * cmax + fabsf(line.l1) * cmax + fabsf(line.l2));
+                    }
+                    const int py0 = (key0 & (W * W - 1)) >> LOGW;
+                    float yr[RPC];
+                    bool maybe = false;
 #pragma unroll
-                        for (int w8 = 0; w8 < 8; ++w8) {
-                            uint32_t wv = 0;
-                            for (int e = 0; e < 4; ++e) {
-                                const int key = key0 + w8 * 4 + e;
-                                if (key < p.lk && mrow[key]) wv |= 1u << (8 * e);
+                    for (int rr = 0; rr < RPC; ++rr) {
+                        yr[rr] = (float)(py0 + rr) * DF + OFFC;          // exact: small integers
+                        // the distance is linear in x: if both row ends are beyond threshold+margin on the same side, no key
+                        // of this image row can satisfy the exact predicate
+                        const float w0 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, OFFC)), line.l2);
+                        const float w1 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, (float)(W - 1) * DF + OFFC)), line.l2);
+                        maybe |= !((w0 > thr_m && w1 > thr_m) || (w0 < -thr_m && w1 < -thr_m));
+                    }
+                    uint32_t bm = 0;
+                    if (__any_sync(0xffffffffu, maybe)) {
+                        uint32_t v[32];
+                        tmem_ld32(t_s + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float xj = (float)(i & (W - 1)) * DF + OFFC;      // compile-time constant
+                            const float wv = __fadd_rn(__fmaf_rn(line.l1, yr[i >> LOGW], __fmul_rn(line.l0, xj)), line.l2);
+                            if (fabsf(wv) < p.epi_thr) {
+                                bm |= 1u << i;
+                                mx = fmaxf(mx, __uint_as_float(v[i]));
                             }
-                            mw[w8] = wv;
                         }
                     }
+                    bits[c] = bm;
+                    anyc |= (__any_sync(0xffffffffu, bm != 0) ? 1u : 0u) << c;
                 }
+            } else {
+                const bool plain = !(epi && main_seg) && !(mrow && main_seg);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = key0 + i;
-                    bool ok = key < klim;
-                    if (mrow && main_seg) ok = ok && ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) != 0;
-                    if (epi && main_seg) {
-                        const int tok = key;
-                        const int t2 = tok / HW;
-                        if (t2 != cur_t2 && ok) {          // uniform across the warp (same key for every lane)
-                            cur_t2 = t2;
-                            line = epi_line(Frow + t2 * 9, xi, yi);
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(t_s + c * 32, v);
+                    tmem_ld_wait();
+                    uint32_t bm = 0;
+                    const int key0 = tile_key0 + c * 32;
+                    if (plain && key0 + 32 <= klim) {             // dense attention, full chunk: no predicate at all
+                        bm = 0xffffffffu;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    } else {
+                        uint32_t mw[8];
+                        if (mrow && main_seg) {
+                            if (key0 + 32 <= p.lk && (p.lk & 15) == 0) {
+                                const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + key0);
+                                const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + key0 + 16);
+                                mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+                                mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+                            } else {
+#pragma unroll
+                                for (int w8 = 0; w8 < 8; ++w8) {
+                                    uint32_t wv = 0;
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int key = key0 + w8 * 4 + e;
+                                        if (key < p.lk && mrow[key]) wv |= 1u << (8 * e);
+                                    }
+                                    mw[w8] = wv;
+                                }
+                            }
                         }
-                        const int pj = tok - t2 * HW;
-                        const float xj = __fadd_rn(__fmul_rn((float)(pj % p.epi_W), (float)p.epi_d), p.epi_off);
-                        const float yj = __fadd_rn(__fmul_rn((float)(pj / p.epi_W), (float)p.epi_d), p.epi_off);
-                        const float dist = fabsf(__fmaf_rn(line.l2, 1.0f, __fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj))));
-                        ok = ok && (dist < p.epi_thr);
+#pragma unroll 4
+                        for (int i = 0; i < 32; ++i) {
+                            const int key = key0 + i;
+                            bool ok = key < klim;
+                            if (mrow && main_seg) ok = ok && ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) != 0;
+                            if (epi && main_seg && ok) {          // generic grid (non power-of-two / 4x4): slow but exact
+                                const int t2 = key / HW;
+                                if (t2 != cur_t2) {
+                                    cur_t2 = t2;
+                                    line = epi_line(Frow + t2 * 9, xi, yi);
+                                }
+                                const int pj = key - t2 * HW;
+                                const float xj = __fadd_rn(__fmul_rn((float)(pj % p.epi_W), (float)p.epi_d), p.epi_off);
+                                const float yj = __fadd_rn(__fmul_rn((float)(pj / p.epi_W), (float)p.epi_d), p.epi_off);
+                                const float dist = fabsf(__fadd_rn(__fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj)), line.l2));
+                                ok = dist < p.epi_thr;
+                            }
+                            if (ok) {
+                                bm |= 1u << i;
+                                mx = fmaxf(mx, __uint_as_float(v[i]));
+                            }
+                        }
                     }
-                    if (ok) {
-                        bm |= 1u << i;
-                        mx = fmaxf(mx, __uint_as_float(v[i]));
-                    }
+                    bits[c] = bm;
                 }
-                bits[c] = bm;
+                anyc = 0xfu;
             }
             const float m_new = fmaxf(m_run, mx * p.scale_log2);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
@@ -264,18 +326,21 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             float lsum = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(t_s + c * 32, v);
-                tmem_ld_wait();
-                const uint32_t bm = bits[c];
+                if ((anyc >> c) & 1u) {
+                    uint32_t v[32];
+                    tmem_ld32(t_s + c * 32, v);
+                    tmem_ld_wait();
+                    const uint32_t bm = bits[c];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float e0 = (bm >> i) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use)) : 0.f;
-                    float e1 = (bm >> (i + 1)) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use)) : 0.f;
-                    // accumulate the row sum from the bf16-rounded values that the PV MMA will actually use
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-                    lsum += __low2float(h) + __high2float(h);
-                    pk[c * 16 + i / 2] = *reinterpret_cast<const uint32_t*>(&h);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float e0 = (bm >> i) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use)) : 0.f;
+                        const float e1 = (bm >> (i + 1)) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use)) : 0.f;
+                        lsum += e0 + e1;
+                        pk[c * 16 + i / 2] = pack_bf16(e0, e1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[c * 16 + i] = 0u;
                 }
             }
             l_run += lsum;
@@ -353,15 +418,28 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
     }
 }
 
-int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
+template <int LOGW, int D>
+static int launch_attn(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        C2V_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        C2V_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<LOGW, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         attr_set = true;
     }
-    attn_tc_kernel<<<dim3(q_tiles, heads, batch), AT_THREADS, AT_SMEM, st>>>(a);
+    attn_tc_kernel<LOGW, D><<<dim3(q_tiles, heads, batch), AT_THREADS, AT_SMEM, st>>>(a);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
+}
+
+int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
+    if (a.epi_F && a.epi_H == a.epi_W && a.lk % AT_BN == 0) {
+        const int w = a.epi_W, d = a.epi_d;
+        if (w == 32 && d == 8) return launch_attn<5, 8>(a, q_tiles, heads, batch, st);
+        if (w == 16 && d == 16) return launch_attn<4, 16>(a, q_tiles, heads, batch, st);
+        if (w == 8 && d == 32) return launch_attn<3, 32>(a, q_tiles, heads, batch, st);
+        if (w == 16 && d == 8) return launch_attn<4, 8>(a, q_tiles, heads, batch, st);
+        if (w == 8 && d == 16) return launch_attn<3, 16>(a, q_tiles, heads, batch, st);
+    }
+    return launch_attn<0, 1>(a, q_tiles, heads, batch, st);
 }
 
 }  // namespace c2v

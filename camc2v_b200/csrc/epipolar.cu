@@ -23,17 +23,24 @@ __global__ void __launch_bounds__(256) epipolar_mask_kernel(const float* __restr
     const int chunks = (int)(L / 16);
     for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
         const int key0 = c * 16;
-        const int t2 = key0 / HW;              // HW is a multiple of 16, so a chunk never straddles frames
-        const float* f = Fm + (((size_t)b * T + t1) * T + t2) * 9;
-        const float a0 = __fmaf_rn(f[2], 1.0f, __fmaf_rn(f[1], yi, __fmul_rn(f[0], xi)));
-        const float a1 = __fmaf_rn(f[5], 1.0f, __fmaf_rn(f[4], yi, __fmul_rn(f[3], xi)));
-        const float a2 = __fmaf_rn(f[8], 1.0f, __fmaf_rn(f[7], yi, __fmul_rn(f[6], xi)));
-        const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
-        const float l0 = __fdiv_rn(a0, nrm), l1 = __fdiv_rn(a1, nrm), l2 = __fdiv_rn(a2, nrm);
+        int cur_t2 = -1;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f;
         uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-            const int pj = key0 - t2 * HW + e;
+            const int t2 = (key0 + e) / HW;            // constant over the chunk whenever HW is a multiple of 16
+            if (t2 != cur_t2) {
+                cur_t2 = t2;
+                const float* f = Fm + (((size_t)b * T + t1) * T + t2) * 9;
+                const float a0 = __fmaf_rn(f[2], 1.0f, __fmaf_rn(f[1], yi, __fmul_rn(f[0], xi)));
+                const float a1 = __fmaf_rn(f[5], 1.0f, __fmaf_rn(f[4], yi, __fmul_rn(f[3], xi)));
+                const float a2 = __fmaf_rn(f[8], 1.0f, __fmaf_rn(f[7], yi, __fmul_rn(f[6], xi)));
+                const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
+                l0 = __fdiv_rn(a0, nrm);
+                l1 = __fdiv_rn(a1, nrm);
+                l2 = __fdiv_rn(a2, nrm);
+            }
+            const int pj = key0 + e - t2 * HW;
             const float xj = __fadd_rn(__fmul_rn((float)(pj % W), (float)d), off);
             const float yj = __fadd_rn(__fmul_rn((float)(pj / W), (float)d), off);
             const float dist = fabsf(__fmaf_rn(l2, 1.0f, __fmaf_rn(l1, yj, __fmul_rn(l0, xj))));
@@ -45,7 +52,7 @@ __global__ void __launch_bounds__(256) epipolar_mask_kernel(const float* __restr
 
 int epipolar_mask_launch(const float* F, uint8_t* out, int B, int T, int H, int W, int d, cudaStream_t st) {
     const int HW = H * W;
-    if (HW % 16 != 0 || B <= 0 || B > 65535) return ERR_UNSUPPORTED;
+    if (((int64_t)T * HW) % 16 != 0 || B <= 0 || B > 65535) return ERR_UNSUPPORTED;
     const float thr = (float)((double)d * sqrt(2.0) / 2.0);
     const float off = (float)d / 2.0f - 0.5f;
     epipolar_mask_kernel<<<dim3(T * HW, B), 256, 0, st>>>(F, out, T, H, W, d, thr, off);

@@ -1,0 +1,163 @@
+"""CPU tests: the oracle (oracle/) against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/*.npz, generated in the build container by oracle/refgen/make_golden.py).
+
+The reference ships no tests of its own; these files are the pin.  Bit-exact for the boolean
+epipolar mask and the camera geometry, fp32 reorder tolerance (1e-5 norm-wise) for the UNet pass.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from camc2v_b200 import synth
+from camc2v_b200.config import UNetConfig
+from camc2v_b200.testing import synth_unet_inputs
+from oracle import camera_oracle, ddim_oracle
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TRAJ = ["pan_yaw", "stationary", "dolly", "yaw", "roll_pan_up", "orbit"]
+
+
+@pytest.fixture(scope="module")
+def masks_gold():
+    return np.load(os.path.join(GOLD, "masks.npz"))
+
+
+def _geometry(kind):
+    K, w2c = synth.synth_camera(kind, T=16)
+    torch.manual_seed(123)
+    rel = camera_oracle.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))
+    return K, rel, camera_oracle.fundamental_matrices(K, rel)
+
+
+@pytest.mark.parametrize("kind", TRAJ)
+def test_geometry_bit_exact(kind, masks_gold):
+    K, rel, Fm = _geometry(kind)
+    if not np.array_equal(rel.numpy(), masks_gold[f"{kind}.rel_c2w"]):
+        # torch.inverse is LAPACK-backed: a different CPU/BLAS build may round differently; the mask tests below
+        # then run on the golden F, which is what pins the mask arithmetic.
+        assert np.allclose(rel.numpy(), masks_gold[f"{kind}.rel_c2w"], rtol=1e-5, atol=1e-6)
+        pytest.skip("4x4 inverse rounds differently on this host; geometry agrees to 1e-5")
+    assert np.array_equal(Fm.numpy(), masks_gold[f"{kind}.F"])
+
+
+@pytest.mark.parametrize("kind", TRAJ)
+@pytest.mark.parametrize("d", [64, 32, 16])
+def test_mask_bit_exact(kind, d, masks_gold):
+    """C restatement of get_epipolar_mask == the reference's mask, bit for bit (sha256 of the packed bits,
+    row/column populations, and the full packed mask for d >= 32)."""
+    Fm = torch.from_numpy(masks_gold[f"{kind}.F"])
+    hw = 256 // d
+    m = oracle.epipolar_mask(Fm, hw, hw, d).numpy()
+    packed = np.packbits(m, axis=-1)
+    assert hashlib.sha256(packed.tobytes()).digest() == masks_gold[f"{kind}.d{d}.sha256"].tobytes()
+    assert np.array_equal(m.sum(-1).astype(np.int32), masks_gold[f"{kind}.d{d}.rowsum"])
+    assert np.array_equal(m.sum(-2).astype(np.int32), masks_gold[f"{kind}.d{d}.colsum"])
+    if d >= 32:
+        assert np.array_equal(packed, masks_gold[f"{kind}.d{d}.packed"])
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("kind", ["pan_yaw", "stationary"])
+def test_mask_bit_exact_full_resolution(kind, masks_gold):
+    Fm = torch.from_numpy(masks_gold[f"{kind}.F"])
+    m = oracle.epipolar_mask(Fm, 32, 32, 8).numpy()
+    assert hashlib.sha256(np.packbits(m, axis=-1).tobytes()).digest() == masks_gold[f"{kind}.d8.sha256"].tobytes()
+    assert np.array_equal(m.sum(-1).astype(np.int32), masks_gold[f"{kind}.d8.rowsum"])
+
+
+def test_mask_edge_cases():
+    # degenerate F (all zeros): lines are 0/0 = NaN, every comparison is false -> empty mask, as in torch
+    Fm = torch.zeros(1, 2, 2, 3, 3)
+    assert not oracle.epipolar_mask(Fm, 4, 4, 64).any()
+    # a line through every pixel row: F such that l = (0, 1, -y0) selects exactly the pixels of one image row
+    Fm = torch.zeros(1, 1, 1, 3, 3)
+    Fm[..., 1, 2] = 1.0      # l1 = 1
+    Fm[..., 2, 2] = -31.5    # l2 = -y0 with y0 = centre of row 0 at d = 64
+    m = oracle.epipolar_mask(Fm, 4, 4, 64)[0]
+    assert m[:, :4].all() and not m[:, 4:].any()
+
+
+@pytest.mark.parametrize("kind", ["pan_yaw", "orbit"])
+def test_plucker_matches_reference(kind, masks_gold):
+    K, _ = synth.synth_camera(kind, T=16)
+    rel = torch.from_numpy(masks_gold[f"{kind}.rel_c2w"])
+    for mode, key in (("plucker", "plucker_sub"), ("ray", "ray_sub")):
+        got = oracle.plucker(K, rel, 256, 256, mode)[..., 3::8, 3::8]
+        assert (got - torch.from_numpy(masks_gold[f"{kind}.{key}"])).abs().max().item() < 1e-6
+
+
+def test_ddim_schedule_known_answers():
+    g = np.load(os.path.join(GOLD, "unet_small.npz"))
+    s = ddim_oracle.ddim_schedule(25, 1.0, "uniform_trailing")
+    assert list(s["timesteps"][:3]) == [39, 79, 119] and s["timesteps"][-1] == 999
+    assert np.array_equal(s["timesteps"].astype(np.float64), g["sched.ddim_timesteps"])
+    for k, gk in (("alphas", "ddim_alphas"), ("alphas_prev", "ddim_alphas_prev"), ("sigmas", "ddim_sigmas"),
+                  ("sqrt_one_minus_alphas", "ddim_sqrt_one_minus_alphas")):
+        assert np.allclose(s[k], g["sched." + gk], rtol=2e-7, atol=0), k
+    assert np.allclose(ddim_oracle.alphas_cumprod(), g["sched.alphas_cumprod"], rtol=2e-7)
+    # SURVEY.md §8c known answers
+    assert abs(s["alphas"][0] - 0.96289510) < 1e-7 and abs(s["alphas"][-1] - 0.00466010) < 1e-7
+    assert abs(s["sigmas"][0] - 0.02883150) < 1e-7 and abs(s["sigmas"][-1] - 0.61106440) < 1e-7
+
+
+@pytest.fixture(scope="module")
+def small():
+    from camc2v_b200.modules import build_unet
+    from oracle.unet_oracle import UNetOracle
+    cfg = UNetConfig(model_channels=64, origin_h=128, origin_w=128)
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in build_unet(cfg).state_dict().items()}
+    sd = synth.synth_state_dict(shapes, 0)
+    g = np.load(os.path.join(GOLD, "unet_small.npz"))
+    inp = synth_unet_inputs(cfg, 16, 2, "small")
+    Fm = torch.from_numpy(g["F"])
+    masks = {d: oracle.epipolar_mask(Fm, 128 // d, 128 // d, d) for d in (8, 16, 32, 64)}
+    cam = {"pluker_embedding_features": inp["pluker"], "sample_locs_dict": masks, "add_type": "add_to_main_branch"}
+    return cfg, UNetOracle(sd, cfg), g, inp, cam
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm()), float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize("key,ctx,use_cam", [("y_cond", "ctx_cond", True), ("y_uncond", "ctx_uncond", True), ("y_nocam", "ctx_cond", False)])
+def test_unet_oracle_matches_reference(small, key, ctx, use_cam):
+    cfg, orc, g, inp, cam = small
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    t = torch.full((1,), 599, dtype=torch.long)
+    y = orc.forward(xc, t, inp[ctx], inp["fs"], cam if use_cam else None)
+    l2, mx = _rel(y, torch.from_numpy(g[key]))
+    assert l2 < 1e-5 and mx < 1e-5, (l2, mx)
+
+
+def test_cfg_step_oracle_matches_reference_sampler(small):
+    """One full p_sample_ddim (cond + uncond pass, CFG 3.5, guidance_rescale 0.7, eta 1) of the reference's DDIMSampler."""
+    cfg, orc, g, inp, cam = small
+    index = int(g["step_index"])
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    t = torch.full((1,), int(g["step_t"]), dtype=torch.long)
+    e_c = orc.forward(xc, t, inp["ctx_cond"], inp["fs"], cam)
+    e_u = orc.forward(xc, t, inp["ctx_uncond"], inp["fs"], cam)
+    torch.manual_seed(20230211)
+    noise = torch.randn(inp["x"].shape)        # the draw the reference makes at ddim.py:340
+    s = ddim_oracle.ddim_schedule()
+    xp, p0 = ddim_oracle.cfg_ddim_update(inp["x"], e_c, e_u, noise, float(s["alphas"][index]), float(s["alphas_prev"][index]),
+                                         float(s["sigmas"][index]), float(s["sqrt_one_minus_alphas"][index]), 3.5, 0.7)
+    assert _rel(xp, torch.from_numpy(g["step_x_prev"]))[0] < 1e-5
+    assert _rel(p0, torch.from_numpy(g["step_pred_x0"]))[0] < 1e-5
+
+
+def test_fused_epipolar_oracle_equals_explicit(small):
+    cfg, orc, g, inp, cam = small
+    from oracle.unet_oracle import UNetOracle
+    fast = UNetOracle(orc.sd, cfg, fused_epipolar=True)
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    t = torch.full((1,), 599, dtype=torch.long)
+    a = fast.forward(xc, t, inp["ctx_cond"], inp["fs"], cam, max_input_block=2)
+    b = orc.forward(xc, t, inp["ctx_cond"], inp["fs"], cam, max_input_block=2)
+    assert _rel(a, b)[0] < 1e-5
