@@ -22,7 +22,7 @@ class GemmDesc(C.Structure):
         ("M", C.c_int), ("N", C.c_int), ("Cin", C.c_int), ("taps", C.c_int),
         ("a_mode", C.c_int), ("nb", C.c_int), ("d1", C.c_int), ("d2", C.c_int),
         ("lda", C.c_int), ("rows_per_group", C.c_int), ("ldr", C.c_int), ("ldo", C.c_int),
-        ("out_bf16", C.c_int), ("epi", C.c_int),
+        ("out_bf16", C.c_int), ("epi", C.c_int), ("splitk", C.c_int), ("ws", C.c_void_p),
     ]
 
 
@@ -47,6 +47,7 @@ PROTOTYPES = {
     "c2v_status_string": (C.c_char_p, [_i]),
     "c2v_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
     "c2v_gemm_tile_n": (_i, [_i, _i]),
+    "c2v_gemm_splitk": (_i, [_i, _i, _i, _i, _i]),
     "c2v_skinny_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "c2v_timestep_embedding": (_i, [_vp, _vp, _i, _i, _vp]),
     "c2v_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),

@@ -40,9 +40,22 @@ int c2v_gemm_tile_n(int N, int epi) {
     return 128;   // ragged last tile: TMA zero fill + masked stores
 }
 
+int c2v_gemm_splitk(int M, int N, int Cin, int taps, int epi) {
+    if (epi != C2V_EPI_LINEAR) return 1;
+    const int bn = c2v_gemm_tile_n(N, epi);
+    const int ctas = ((M + 127) / 128) * ((N + bn - 1) / bn);
+    const int iters = taps * (Cin / 64);
+    if (ctas >= 96 || iters < 40) return 1;
+    int s = (296 + ctas - 1) / ctas;
+    if (s > 8) s = 8;
+    if (s > iters / 5) s = iters / 5;
+    return s < 2 ? 1 : s;
+}
+
 int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     if (!d || !d->a || !d->w || !d->out) return ERR_BAD_ARG;
-    if (d->M <= 0 || d->N <= 0 || d->Cin <= 0 || d->Cin % 64 != 0) return ERR_UNSUPPORTED;
+    if (d->M <= 0 || d->N <= 0 || d->Cin <= 0 || d->Cin % 64 != 0 || d->N % 4 != 0) return ERR_UNSUPPORTED;
+    if (d->ldo % 4 != 0 || (d->residual && d->ldr % 4 != 0)) return ERR_UNSUPPORTED;
     if (d->taps != 1 && d->taps != 3 && d->taps != 9) return ERR_BAD_ARG;
     if (d->rowbias && d->rows_per_group <= 0) return ERR_BAD_ARG;
     const int bn = c2v_gemm_tile_n(d->N, d->epi);
@@ -65,6 +78,11 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     a.out = d->out;
     a.ldo = d->ldo;
     a.out_bf16 = d->out_bf16;
+    a.splits = d->splitk > 1 ? d->splitk : 1;
+    if (a.splits > 1) {
+        if (!d->ws || d->epi != C2V_EPI_LINEAR || a.splits > a.taps * a.k_chunks) return ERR_BAD_ARG;
+        a.out = d->ws;
+    }
 
     if (d->a_mode == C2V_A_PLAIN) {
         if (d->taps != 1 || d->lda < d->Cin) return ERR_BAD_ARG;
@@ -131,7 +149,10 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     const int m_tiles = (d->M + a.tile_rows - 1) / a.tile_rows;
     const int n_tiles = (d->N + bn - 1) / bn;
     if (n_tiles > 65535) return ERR_UNSUPPORTED;
-    return gemm_tc_launch(a, bn, m_tiles, n_tiles, (cudaStream_t)stream);
+    const int rc = gemm_tc_launch(a, bn, m_tiles, n_tiles, (cudaStream_t)stream);
+    if (rc != OK || a.splits == 1) return rc;
+    return splitk_reduce_launch(d->ws, a.splits, d->M, d->N, d->bias, d->rowbias, a.rows_per_group, d->residual, d->ldr, d->out, d->ldo,
+                                d->out_bf16, (cudaStream_t)stream);
 }
 
 int c2v_skinny_linear(const float* in, const void* w, const float* bias, float* out, int M, int N, int K, int silu_in, void* stream) {

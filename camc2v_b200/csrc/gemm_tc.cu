@@ -47,7 +47,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     const int warp = threadIdx.x >> 5;
     const int m_tile = blockIdx.x;
     const int n0 = blockIdx.y * BN;
-    const int iters = p.taps * p.k_chunks;
+    const int total_iters = p.taps * p.k_chunks;
+    const int it_begin = (int)((long long)total_iters * blockIdx.z / p.splits);
+    const int it_end = (int)((long long)total_iters * (blockIdx.z + 1) / p.splits);
+    const int iters = it_end - it_begin;
     constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
 
     if (threadIdx.x == 0) {
@@ -89,30 +92,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                 c1 = m0 % p.dim1;
             }
             const uint32_t tx = (uint32_t)p.tile_rows * BK * 2 + S::B_BYTES;
-            int it = 0;
-            for (int tap = 0; tap < p.taps; ++tap) {
+            for (int it = 0; it < iters; ++it) {
+                const int git = it_begin + it;
+                const int tap = git / p.k_chunks, kc = git - tap * p.k_chunks;
                 int d1 = 0, d2 = 0;
-                if (p.a_mode == A_CONV2D) {
-                    d1 = tap % 3 - 1;
-                    d2 = tap / 3 - 1;
-                    if (p.taps == 1) d1 = d2 = 0;
-                } else if (p.a_mode == A_CONVT) {
-                    d2 = tap - 1;
-                    if (p.taps == 1) d2 = 0;
+                if (p.taps > 1) {
+                    if (p.a_mode == A_CONV2D) {
+                        d1 = tap % 3 - 1;
+                        d2 = tap / 3 - 1;
+                    } else if (p.a_mode == A_CONVT) {
+                        d2 = tap - 1;
+                    }
                 }
-                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-                    uint8_t* b_dst = a_dst + S::A_BYTES;
-                    mbar_expect_tx(&full_bar[s], tx);
-                    if (p.a_mode == A_PLAIN)
-                        tma_load_2d(a_dst, &p.tmA, &full_bar[s], kc * BK, c1);
-                    else
-                        tma_load_4d(a_dst, &p.tmA, &full_bar[s], kc * BK, c1 + d1, c2 + d2, c3);
-                    tma_load_2d(b_dst, &p.tmB, &full_bar[s], (tap * p.k_chunks + kc) * BK, n0);
-                }
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + S::A_BYTES;
+                mbar_expect_tx(&full_bar[s], tx);
+                if (p.a_mode == A_PLAIN)
+                    tma_load_2d(a_dst, &p.tmA, &full_bar[s], kc * BK, c1);
+                else
+                    tma_load_4d(a_dst, &p.tmA, &full_bar[s], kc * BK, c1 + d1, c2 + d2, c3);
+                tma_load_2d(b_dst, &p.tmB, &full_bar[s], git * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -147,7 +149,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         mbar_wait(acc_bar, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
-        const float* rb = (p.rowbias && row_ok) ? p.rowbias + (size_t)(m / p.rows_per_group) * p.N : nullptr;
+        const bool part = p.splits > 1;                 // split-K: store the raw fp32 partial tile, epilogue terms are applied by the reduce
+        const float* rb = (!part && p.rowbias && row_ok) ? p.rowbias + (size_t)(m / p.rows_per_group) * p.N : nullptr;
+        const float* bias = part ? nullptr : p.bias;
+        const float* resid = part ? nullptr : p.residual;
+        const int out_bf16 = part ? 0 : p.out_bf16;
+        const int ldo = part ? p.N : p.ldo;
+        void* const outp = part ? (void*)(reinterpret_cast<float*>(p.out) + (size_t)blockIdx.z * p.M * p.N) : p.out;
         if (p.epi == EPI_GEGLU) {
             constexpr int HALF = BN / 2;
             const int no = blockIdx.y * HALF;          // output column base
@@ -189,10 +197,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                     const int nvalid = min(32, p.N - (n0 + c));
                     if (nvalid == 32) {
-                        if (p.bias) {
+                        if (bias) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n0 + c + j);
+                                const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c + j);
                                 f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                             }
                         }
@@ -203,22 +211,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                                 f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                             }
                         }
-                        if (p.residual) {
-                            const float* rs = p.residual + (size_t)m * p.ldr + n0 + c;
+                        if (resid) {
+                            const float* rs = resid + (size_t)m * p.ldr + n0 + c;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 b4 = *reinterpret_cast<const float4*>(rs + j);
                                 f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                             }
                         }
-                        if (p.out_bf16) {
-                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n0 + c;
+                        if (out_bf16) {
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + (size_t)m * ldo + n0 + c;
 #pragma unroll
                             for (int j = 0; j < 32; j += 8)
                                 *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
                                                                               pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
                         } else {
-                            float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n0 + c;
+                            float* o = reinterpret_cast<float*>(outp) + (size_t)m * ldo + n0 + c;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                         }
@@ -227,13 +235,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                         for (int j = 0; j < nvalid; ++j) {
                             float x = f[j];
                             const int n = n0 + c + j;
-                            if (p.bias) x += p.bias[n];
+                            if (bias) x += bias[n];
                             if (rb) x += rb[n];
-                            if (p.residual) x += p.residual[(size_t)m * p.ldr + n];
-                            if (p.out_bf16)
-                                reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)m * p.ldo + n] = __float2bfloat16(x);
+                            if (resid) x += resid[(size_t)m * p.ldr + n];
+                            if (out_bf16)
+                                reinterpret_cast<__nv_bfloat16*>(outp)[(size_t)m * ldo + n] = __float2bfloat16(x);
                             else
-                                reinterpret_cast<float*>(p.out)[(size_t)m * p.ldo + n] = x;
+                                reinterpret_cast<float*>(outp)[(size_t)m * ldo + n] = x;
                         }
                     }
                 }
@@ -256,7 +264,52 @@ static int launch(const GemmKernelArgs& a, int m_tiles, int n_tiles, cudaStream_
         C2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
-    gemm_tc_kernel<BN><<<dim3(m_tiles, n_tiles), GEMM_THREADS, S::TOTAL, st>>>(a);
+    gemm_tc_kernel<BN><<<dim3(m_tiles, n_tiles, a.splits), GEMM_THREADS, S::TOTAL, st>>>(a);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// out = sum_z ws[z] + bias + rowbias + residual  (deterministic split-K reduction, fused epilogue)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, const float* __restrict__ bias,
+                                                            const float* __restrict__ rowbias, int rows_per_group,
+                                                            const float* __restrict__ residual, int ldr, void* __restrict__ out, int ldo,
+                                                            int out_bf16) {
+    const int nv = N >> 2;
+    const size_t plane = (size_t)M * N;
+    const long long total = (long long)M * nv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / nv);
+        const int n = (int)(i - (long long)m * nv) * 4;
+        float4 x = *reinterpret_cast<const float4*>(ws + (size_t)m * N + n);
+        for (int z = 1; z < splits; ++z) {
+            const float4 y = *reinterpret_cast<const float4*>(ws + z * plane + (size_t)m * N + n);
+            x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+        }
+        if (bias) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + n);
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+        }
+        if (rowbias) {
+            const float4 b = *reinterpret_cast<const float4*>(rowbias + (size_t)(m / rows_per_group) * N + n);
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+        }
+        if (residual) {
+            const float4 b = *reinterpret_cast<const float4*>(residual + (size_t)m * ldr + n);
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+        }
+        if (out_bf16)
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)m * ldo + n) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+        else
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)m * ldo + n) = x;
+    }
+}
+
+int splitk_reduce_launch(const float* ws, int splits, int M, int N, const float* bias, const float* rowbias, int rows_per_group,
+                         const float* residual, int ldr, void* out, int ldo, int out_bf16, cudaStream_t st) {
+    long long work = (long long)M * (N >> 2);
+    int grid = (int)((work + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    splitk_reduce_kernel<<<grid, 256, 0, st>>>(ws, splits, M, N, bias, rowbias, rows_per_group, residual, ldr, out, ldo, out_bf16);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -26,8 +26,11 @@ struct GemmKernelArgs {
     void* out;              // fp32 or bf16 [M, ldo]
     int ldo;
     int out_bf16;
+    int splits;             // split-K factor (grid.z); > 1: raw fp32 partials go to `out` = ws[z][M][N]
 };
 
 int gemm_tc_launch(const GemmKernelArgs& a, int bn, int m_tiles, int n_tiles, cudaStream_t st);
+int splitk_reduce_launch(const float* ws, int splits, int M, int N, const float* bias, const float* rowbias, int rows_per_group,
+                         const float* residual, int ldr, void* out, int ldo, int out_bf16, cudaStream_t st);
 
 }  // namespace c2v

@@ -40,11 +40,14 @@ __device__ __forceinline__ GnMap gn_map(int C) {
 }
 
 // partial (sum, sumsq) per (sample, slab, group)
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws, int rows, int C,
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws, int rows, int C,
                                                               int rows_per_slab) {
-    __shared__ float s_sum[32], s_sq[32];
+    // Per-thread fp32 partials are combined across the CTA as 64-bit fixed point: integer atomics are
+    // order-independent, so the statistics (and everything downstream) are bit-reproducible run to run.
+    __shared__ long long s_sum[32], s_sq[32];
+    constexpr float SUM_SCALE = 262144.f, SQ_SCALE = 1024.f;     // 2^18, 2^10
     const int n = blockIdx.y, slab = blockIdx.x, nslab = gridDim.x;
-    if (threadIdx.x < 32) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0.f;
+    if (threadIdx.x < 32) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0;
     __syncthreads();
     const GnMap m = gn_map(C);
     const int cg = C / 32;
@@ -56,8 +59,23 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
             const int cv = m.cv0 + s * GN_THREADS;
             if (cv >= m.nvec) break;
             float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int r = r0 + m.rsub; r < r1; r += m.rows_par) {
-                const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)r * C + cv * 4);
+            const float* col = xs + cv * 4;
+            const size_t step = (size_t)m.rows_par * C;
+            int r = r0 + m.rsub;
+            // 4 independent 16-byte loads in flight per thread
+            for (; r + 3 * m.rows_par < r1; r += 4 * m.rows_par) {
+                const float* p0 = col + (size_t)r * C;
+                const float4 v0 = *reinterpret_cast<const float4*>(p0);
+                const float4 v1 = *reinterpret_cast<const float4*>(p0 + step);
+                const float4 v2 = *reinterpret_cast<const float4*>(p0 + 2 * step);
+                const float4 v3 = *reinterpret_cast<const float4*>(p0 + 3 * step);
+                a[0] += (v0.x + v1.x) + (v2.x + v3.x); q[0] += fmaf(v0.x, v0.x, v1.x * v1.x) + fmaf(v2.x, v2.x, v3.x * v3.x);
+                a[1] += (v0.y + v1.y) + (v2.y + v3.y); q[1] += fmaf(v0.y, v0.y, v1.y * v1.y) + fmaf(v2.y, v2.y, v3.y * v3.y);
+                a[2] += (v0.z + v1.z) + (v2.z + v3.z); q[2] += fmaf(v0.z, v0.z, v1.z * v1.z) + fmaf(v2.z, v2.z, v3.z * v3.z);
+                a[3] += (v0.w + v1.w) + (v2.w + v3.w); q[3] += fmaf(v0.w, v0.w, v1.w * v1.w) + fmaf(v2.w, v2.w, v3.w * v3.w);
+            }
+            for (; r < r1; r += m.rows_par) {
+                const float4 v = *reinterpret_cast<const float4*>(col + (size_t)r * C);
                 a[0] += v.x; q[0] = fmaf(v.x, v.x, q[0]);
                 a[1] += v.y; q[1] = fmaf(v.y, v.y, q[1]);
                 a[2] += v.z; q[2] = fmaf(v.z, v.z, q[2]);
@@ -65,14 +83,16 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
             }
             const int g0 = (cv * 4) / cg, g3 = (cv * 4 + 3) / cg;
             if (g0 == g3) {
-                atomicAdd(&s_sum[g0], a[0] + a[1] + a[2] + a[3]);
-                atomicAdd(&s_sq[g0], q[0] + q[1] + q[2] + q[3]);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g0]),
+                          (unsigned long long)__float2ll_rn(((a[0] + a[1]) + (a[2] + a[3])) * SUM_SCALE));
+                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sq[g0]),
+                          (unsigned long long)__float2ll_rn(((q[0] + q[1]) + (q[2] + q[3])) * SQ_SCALE));
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int g = (cv * 4 + e) / cg;
-                    atomicAdd(&s_sum[g], a[e]);
-                    atomicAdd(&s_sq[g], q[e]);
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g]), (unsigned long long)__float2ll_rn(a[e] * SUM_SCALE));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&s_sq[g]), (unsigned long long)__float2ll_rn(q[e] * SQ_SCALE));
                 }
             }
         }
@@ -80,12 +100,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
     __syncthreads();
     if (threadIdx.x < 32) {
         float* w = ws + (((size_t)n * nslab + slab) * 32 + threadIdx.x) * 2;
-        w[0] = s_sum[threadIdx.x];
-        w[1] = s_sq[threadIdx.x];
+        w[0] = (float)((double)s_sum[threadIdx.x] * (1.0 / SUM_SCALE));
+        w[1] = (float)((double)s_sq[threadIdx.x] * (1.0 / SQ_SCALE));
     }
 }
 
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ ws,
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ ws,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               __nv_bfloat16* __restrict__ out, int rows, int C, int rows_per_slab,
                                                               float eps, int silu) {
@@ -124,21 +144,34 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
             sc[e] = s_rstd[g] * gamma[c];
             sh[e] = beta[c] - s_mean[g] * sc[e];
         }
-        for (int r = r0 + m.rsub; r < r1; r += m.rows_par) {
-            const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)r * C + cv * 4);
+        const size_t step = (size_t)m.rows_par * C;
+        const float* col = xs + cv * 4;
+        __nv_bfloat16* ocol = os + cv * 4;
+        auto emit = [&](const float4 v, size_t off) {
             float y0 = fmaf(v.x, sc[0], sh[0]), y1 = fmaf(v.y, sc[1], sh[1]), y2 = fmaf(v.z, sc[2], sh[2]), y3 = fmaf(v.w, sc[3], sh[3]);
             if (silu) {
                 y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3);
             }
-            *reinterpret_cast<uint2*>(os + (size_t)r * C + cv * 4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+            *reinterpret_cast<uint2*>(ocol + off) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+        };
+        int r = r0 + m.rsub;
+        for (; r + 3 * m.rows_par < r1; r += 4 * m.rows_par) {
+            const size_t o0 = (size_t)r * C;
+            const float4 v0 = *reinterpret_cast<const float4*>(col + o0);
+            const float4 v1 = *reinterpret_cast<const float4*>(col + o0 + step);
+            const float4 v2 = *reinterpret_cast<const float4*>(col + o0 + 2 * step);
+            const float4 v3 = *reinterpret_cast<const float4*>(col + o0 + 3 * step);
+            emit(v0, o0); emit(v1, o0 + step); emit(v2, o0 + 2 * step); emit(v3, o0 + 3 * step);
         }
+        for (; r < r1; r += m.rows_par) emit(*reinterpret_cast<const float4*>(col + (size_t)r * C), (size_t)r * C);
     }
 }
 
 static int gn_slabs(int ns, int rows, int* rows_per_slab) {
-    int target = 592 / (ns > 0 ? ns : 1);
+    // ~2 CTAs per SM in total, but never fewer than 16 rows per CTA (each thread wants several rows in flight)
+    int target = 296 / (ns > 0 ? ns : 1);
     if (target < 1) target = 1;
-    int slabs = (rows + 7) / 8;
+    int slabs = (rows + 15) / 16;
     if (slabs > target) slabs = target;
     if (slabs < 1) slabs = 1;
     *rows_per_slab = (rows + slabs - 1) / slabs;

@@ -572,6 +572,10 @@ class BasicTransformerBlock(_Prepared):
                 p[name] = (_bf16(lin.weight), _f32(lin.bias))
         return p
 
+    def origin_h(self) -> int:
+        """Pixel size of the full frame the epipolar grid refers to (Epipolar.origin_h, epipolar.py:112-113)."""
+        return self.epipolar.origin_h if hasattr(self, "epipolar") else 256
+
     def forward_spatial(self, x: torch.Tensor, ctx: ContextPack, bq: int, lq: int):
         """x fp32 CL [bq*lq, C] -> bf16 (the only consumer is proj_out)."""
         p = self.pk()
@@ -637,11 +641,10 @@ class BasicTransformerBlock(_Prepared):
         if camera_condition is not None:
             H, W = camera_condition["h"], camera_condition["w"]
             B = b // (H * W)
-            cam = camera_level_from_condition(camera_condition, B, nq, H, W, x.device)
+            cam = camera_level_from_condition(camera_condition, B, nq, H, W, x.device, self.origin_h())
             dm = Dims(B, nq, H, W)
         else:
             dm = Dims(1, nq, hw_b, 1)
-        xs = _transpose_tokens(_f32(x).view(dm.B, dm.HW, nq, c).reshape(dm.B * dm.HW * nq, c), 1, 1)
         xs = _f32(x).view(dm.B, dm.HW, nq, c).permute(0, 2, 1, 3).reshape(dm.M, c).contiguous()
         y = self.forward_temporal(xs, dm, cam).float()
         return y.view(dm.B, nq, dm.HW, c).permute(0, 2, 1, 3).reshape(b, nq, c)
@@ -767,7 +770,9 @@ class TemporalTransformer(_Prepared):
     def forward(self, x, context=None, camera_condition=None):
         b, c, t, hh, ww = x.shape
         h = ops.to_channels_last(_f32(x), b, c, t * hh * ww)
-        cam = camera_level_from_condition(camera_condition, b, t, hh, ww, x.device) if camera_condition is not None else None
+        cam = None
+        if camera_condition is not None:
+            cam = camera_level_from_condition(camera_condition, b, t, hh, ww, x.device, self.transformer_blocks[0].origin_h())
         y = self.forward_cl(h, Dims(b, t, hh, ww), cam)
         return ops.from_channels_last(y, b, c, t * hh * ww).view(b, c, t, hh, ww)
 

@@ -51,6 +51,11 @@ def _gemm(a, w, M, N, Cin, taps, a_mode, nb, d1, d2, lda, bias, rowbias, rows_pe
     d.ldo = out.stride(0)
     d.out_bf16 = 1 if out.dtype == BF16 else 0
     d.epi = epi
+    sk = _lib.load().c2v_gemm_splitk(M, N, Cin, taps, epi)
+    if sk > 1:
+        ws = torch.empty((sk, M, N), device=a.device, dtype=F32)
+        d.splitk, d.ws = sk, _p(ws)
+        _lib.LAUNCHES += 1          # the deterministic split-K reduction kernel
     _lib.call("c2v_gemm", C.byref(d), _stream())
     return out
 

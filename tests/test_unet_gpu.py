@@ -186,7 +186,8 @@ def test_full_unet_vs_reference_golden(full, key, ctx):
 
 
 def test_full_unet_batch2_is_two_independent_samples(full):
-    """Size-independent property: the path shards by video, so a batch of two videos equals the two run alone."""
+    """Size-independent property: the path shards by video, so a batch of two videos equals the two run alone
+    (up to the bf16 noise floor: tile / split-K schedules, hence fp32 summation orders, depend on the batch size)."""
     cfg, unet, g, inp, cam = full
     xc = torch.cat([inp["x"], inp["c_concat"]], dim=1).to(DEV)
     x2 = torch.cat([xc, xc.flip(2)], dim=0)
@@ -201,4 +202,5 @@ def test_full_unet_batch2_is_two_independent_samples(full):
         cam1 = {"pluker_embedding_features": [p[i:i + 1].contiguous() for p in cam2["pluker_embedding_features"]],
                 "epipolar_F": cam2["epipolar_F"][i:i + 1].contiguous(), "add_type": "add_to_main_branch"}
         y1 = unet(x2[i:i + 1].contiguous(), t[i:i + 1], context=ctx2[i:i + 1].contiguous(), fs=fs[i:i + 1], camera_condition=cam1)
-        assert torch.equal(y1[0], y2[i])
+        l2, mx = rel(y1[0], y2[i])
+        assert l2 < TOL_L2 and mx < TOL_MAX, (i, l2, mx)
