@@ -146,6 +146,33 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
         const uint32_t box[2] = {64, (uint32_t)bn};
         if (!make_tmap_bf16(&a.tmB, d->w, 2, dims, strides, box)) return ERR_TMA_ENCODE;
     }
+    if (d->epi == C2V_EPI_LINEAR) {
+        // TMA epilogue descriptors (residual load, output / split-K partial store).  When the output rows are not 16-byte
+        // aligned (e.g. a 4-column bf16 output) the kernel falls back to its direct-store epilogue.
+        const bool part = a.splits > 1;
+        const bool o_f32 = part || !d->out_bf16;
+        const void* obase = part ? (const void*)d->ws : (const void*)d->out;
+        const uint64_t ld = part ? (uint64_t)d->N : (uint64_t)d->ldo;
+        const uint64_t esz = o_f32 ? 4 : 2;
+        bool ok = (ld * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0;
+        if (d->residual && !part) ok = ok && ((uint64_t)d->ldr * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0;
+        if (ok) {
+            const uint64_t odims[3] = {(uint64_t)d->N, (uint64_t)d->M, (uint64_t)a.splits};
+            const uint64_t ostr[2] = {ld * esz, (uint64_t)d->M * ld * esz};
+            const uint32_t obox[3] = {32, (uint32_t)a.tile_rows, 1};
+            if (!make_tmap(&a.tmO, obase, 3, odims, ostr, obox, o_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                           o_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+                return ERR_TMA_ENCODE;
+            if (d->residual && !part) {
+                const uint64_t rdims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+                const uint64_t rstr[1] = {(uint64_t)d->ldr * 4};
+                const uint32_t rbox[2] = {32, (uint32_t)a.tile_rows};
+                if (!make_tmap(&a.tmR, d->residual, 2, rdims, rstr, rbox, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B))
+                    return ERR_TMA_ENCODE;
+            }
+            a.tma_epi = 1;
+        }
+    }
     const int m_tiles = (d->M + a.tile_rows - 1) / a.tile_rows;
     const int n_tiles = (d->N + bn - 1) / bn;
     if (n_tiles > 65535) return ERR_UNSUPPORTED;

@@ -31,7 +31,7 @@ struct GemmSmem {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 128 + 1024;  // + barriers/tmem ptr + 1024B alignment slack
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers/tmem ptr + 1024B alignment slack
 };
 
 template <int BN>
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_bar = empty_bar + STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    uint64_t* res_bar = acc_bar + 2;                      // [BN / 32] residual-chunk arrival barriers (TMA epilogue)
 
     const int warp = threadIdx.x >> 5;
     const int m_tile = blockIdx.x;
@@ -61,6 +62,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(acc_bar, 1);
+        for (int c = 0; c < BN / 32; ++c) mbar_init(&res_bar[c], 1);
+        if (p.tma_epi) {
+            tma_prefetch_desc(&p.tmO);
+            if (p.residual && p.splits == 1) tma_prefetch_desc(&p.tmR);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -146,12 +152,92 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         const int r = lg * 32 + lane_id();             // row inside the tile
         const int m = m_tile * p.tile_rows + r;
         const bool row_ok = (r < p.tile_rows) && (m < p.M);
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
         const bool part = p.splits > 1;                 // split-K: store the raw fp32 partial tile, epilogue terms are applied by the reduce
+        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
         const float* rb = (!part && p.rowbias && row_ok) ? p.rowbias + (size_t)(m / p.rows_per_group) * p.N : nullptr;
         const float* bias = part ? nullptr : p.bias;
+        if (p.tma_epi) {
+            // ---- TMA epilogue: residual tile fetched by TMA into the (now idle) pipeline stages with every 32-column chunk
+            //      in flight at once; results staged in shared memory (hardware swizzle, conflict-free) and written back by
+            //      TMA stores, so every global access of the epilogue is a full-line bulk transfer.
+            constexpr int NCH = BN / 32;
+            const int m0 = m_tile * p.tile_rows;
+            const bool has_res = p.residual != nullptr && !part;
+            const bool out_f32 = part || !p.out_bf16;
+            const bool leader = threadIdx.x == 64;      // warp 2, lane 0: owns the bulk async-group of the stores
+            mbar_wait(acc_bar, 0);                      // every MMA has completed: accumulator valid, smem stages free
+            tc_fence_after();
+            if (leader && has_res) {
+                for (int c = 0; c < NCH; ++c) {
+                    if (n0 + c * 32 >= p.N) break;
+                    mbar_expect_tx(&res_bar[c], (uint32_t)p.tile_rows * 128);
+                    tma_load_2d(smem + c * 16384, &p.tmR, &res_bar[c], n0 + c * 32, m0);
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                if (n0 + c * 32 >= p.N) break;          // CTA-uniform
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+                tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                uint8_t* buf = smem + c * 16384;
+                uint8_t* rowp = buf + r * 128;
+                if (has_res) {
+                    mbar_wait(&res_bar[c], 0);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 x = *reinterpret_cast<const float4*>(rowp + ((k ^ (r & 7)) << 4));
+                        f[4 * k] += x.x; f[4 * k + 1] += x.y; f[4 * k + 2] += x.z; f[4 * k + 3] += x.w;
+                    }
+                }
+                const int nb = n0 + c * 32;
+                if (bias) {
+                    if (nb + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias + nb + j);
+                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.N) f[j] += bias[nb + j];
+                    }
+                }
+                if (rb) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(rb + nb + j);
+                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    }
+                }
+                if (out_f32) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        *reinterpret_cast<float4*>(rowp + ((k ^ (r & 7)) << 4)) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+                } else {
+                    if (has_res) named_bar_sync(1, 128);        // bf16 rows are packed tighter than the fp32 residual rows they replace
+                    uint8_t* orow = buf + r * 64;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<uint4*>(orow + ((k ^ ((r >> 1) & 3)) << 4)) =
+                            make_uint4(pack_bf16(f[8 * k], f[8 * k + 1]), pack_bf16(f[8 * k + 2], f[8 * k + 3]),
+                                       pack_bf16(f[8 * k + 4], f[8 * k + 5]), pack_bf16(f[8 * k + 6], f[8 * k + 7]));
+                }
+                fence_proxy_async();
+                named_bar_sync(1, 128);
+                if (leader) {
+                    tma_store_3d(&p.tmO, buf, nb, m0, blockIdx.z);
+                    tma_store_commit();
+                }
+            }
+            if (leader) tma_store_wait_read_all();
+            tc_fence_before();
+        } else {
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
         const float* resid = part ? nullptr : p.residual;
         const int out_bf16 = part ? 0 : p.out_bf16;
         const int ldo = part ? p.N : p.ldo;
@@ -248,6 +334,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             }
         }
         tc_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {

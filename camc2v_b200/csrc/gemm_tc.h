@@ -11,6 +11,9 @@ enum EpiMode : int { EPI_LINEAR = 0, EPI_GEGLU = 1 };
 struct GemmKernelArgs {
     CUtensorMap tmA;        // activations (bf16): rank 2 [K, M] or rank 4 (C, W, H, N) / (C, HW, T, B)
     CUtensorMap tmB;        // weights (bf16) [N, taps*Cin], K-major
+    CUtensorMap tmR;        // residual (fp32) [M, ldr], box (32, tile_rows), 128B swizzle   (EPI_LINEAR with residual)
+    CUtensorMap tmO;        // output [splits, M, ldo]: fp32 box (32, tile_rows, 1) SW128 | bf16 box (32, tile_rows, 1) SW64
+    int tma_epi;            // 1: EPI_LINEAR epilogue goes through TMA (tmR / tmO valid)
     int M, N;               // output rows / columns
     int k_chunks;           // Cin / 64
     int taps;               // 1, 3 (temporal conv) or 9 (3x3 conv)

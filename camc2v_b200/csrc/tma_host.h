@@ -24,8 +24,16 @@ inline PFN_encodeTiled get_encode_fn() {
 }
 
 // dims[0] is the contiguous dimension (elements); strides_bytes[i] is the byte stride of dims[i+1].
+inline bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMapDataType dtype, CUtensorMapSwizzle swz);
+
 inline bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box) {
+    return make_tmap(m, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+inline bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMapDataType dtype, CUtensorMapSwizzle swz) {
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t gd[5];
@@ -37,9 +45,8 @@ inline bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uin
         es[i] = 1;
     }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 

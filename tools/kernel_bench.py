@@ -121,7 +121,39 @@ def bench_attn():
         print(f"  {B:3d} {T:3d} {HW:5d} {h:3d}  {us:8.1f} us  {B * T * HW * h * 64 * 2 * 4 / us / 1e3:7.1f} GB/s")
 
 
+def single(which):
+    """One representative launch series (for `ncu --set full -s 3 -c 1`)."""
+    from camc2v_b200 import camera, synth
+    if which == "lin0":
+        a, w, b, r = rb(16384, 320), rb(320, 320), rb(320, dtype=torch.float32), rb(16384, 320, dtype=torch.float32)
+        fn = lambda: ops.linear(a, w, bias=b, residual=r)
+    elif which == "conv0":
+        a, w, b, r = rb(16384, 320), rb(320, 2880), rb(320, dtype=torch.float32), rb(16384, 320, dtype=torch.float32)
+        fn = lambda: ops.conv3x3(a, w, 16, 32, 32, bias=b, residual=r)
+    elif which == "gn0":
+        x, g, b = rb(16384, 320, dtype=torch.float32), rb(320, dtype=torch.float32), rb(320, dtype=torch.float32)
+        fn = lambda: ops.groupnorm(x, g, b, 16, 1024, 1e-5, True)
+    elif which == "epi0":
+        T, H, d, h = 16, 32, 8, 5
+        L, C = T * H * H, h * 64
+        qkv, reg = rb(L, 3 * C), rb(4, 2 * C)
+        K, w2c = synth.synth_camera("pan_yaw", T=T)
+        torch.manual_seed(123)
+        Fm = camera.fundamental_matrices(K, camera.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))).to(DEV).contiguous()
+        fn = lambda: ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], 1, L, L, h, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm,
+                                   epi_grid=(T, H, H), epi_d=d)
+    elif which == "attn0":
+        q, kv = rb(16 * 1024, 320), rb(16 * 1024, 640)
+        fn = lambda: ops.attention(q, kv[:, :320], kv[:, 320:], 16, 1024, 1024, 5)
+    else:
+        raise SystemExit(which)
+    print(which, f"{timeit(fn):.1f} us")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "single":
+        single(sys.argv[2])
+        sys.exit(0)
     which = sys.argv[1:] or ["gemm", "conv", "norm", "attn"]
     torch.manual_seed(0)
     if "gemm" in which:
