@@ -41,14 +41,16 @@ int c2v_gemm_tile_n(int N, int epi) {
 }
 
 int c2v_gemm_splitk(int M, int N, int Cin, int taps, int epi) {
+    // Fill the machine (148 SMs x 2 resident CTAs) when the output has few tiles but the K loop is deep: the 16x16, 8x8 and
+    // 4x4 levels of the UNet at batch 1.  Each split keeps >= 15 K-iterations so the partial-tile traffic stays amortised.
     if (epi != C2V_EPI_LINEAR) return 1;
     const int bn = c2v_gemm_tile_n(N, epi);
     const int ctas = ((M + 127) / 128) * ((N + bn - 1) / bn);
     const int iters = taps * (Cin / 64);
-    if (ctas >= 96 || iters < 40) return 1;
-    int s = (296 + ctas - 1) / ctas;
+    if (ctas >= 200 || iters < 30) return 1;
+    int s = (296 + ctas / 2) / ctas;           // round to the nearest multiple of one full wave
     if (s > 8) s = 8;
-    if (s > iters / 5) s = iters / 5;
+    if (s > iters / 15) s = iters / 15;
     return s < 2 ? 1 : s;
 }
 

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j % AT_KV_STAGES;
                 const uint32_t ph = (j / AT_KV_STAGES) & 1;
-                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_wait<200>(&kv_empty[s], ph ^ 1);
                 mbar_expect_tx(&kv_full[s], AT_K_BYTES + AT_V_BYTES);
                 if (j < n_main) {
                     tma_load_3d(smem + AT_OFF_K + s * AT_K_BYTES, &p.tmK, &kv_full[s], head * AT_D, j * AT_BN, bkv);
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         const uint32_t p_addr = smem_u32(smem + AT_OFF_P);
         auto issue_qk = [&](int j) {
             const int s = j % AT_KV_STAGES;
-            mbar_wait(&kv_full[s], (j / AT_KV_STAGES) & 1);
-            if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+            mbar_wait<40>(&kv_full[s], (j / AT_KV_STAGES) & 1);
+            if (j > 0) mbar_wait<40>(s_free, (j - 1) & 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t qd = umma_desc_sw128(q_addr);
@@ -153,12 +153,12 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             }
             __syncwarp();
         };
-        mbar_wait(q_full, 0);
+        mbar_wait<40>(q_full, 0);
         issue_qk(0);
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j % AT_KV_STAGES;
             if (j + 1 < n_tiles) issue_qk(j + 1);     // overlaps with the softmax warps writing P(j)
-            mbar_wait(p_full, j & 1);
+            mbar_wait<40>(p_full, j & 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t v_addr = smem_u32(smem + AT_OFF_V + s * AT_V_BYTES);

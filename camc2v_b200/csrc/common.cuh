@@ -55,12 +55,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps after ~2 s instead of hanging the GPU.
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+// SLEEP_NS > 0 backs off with nanosleep between polls: used by the warps that only orchestrate (TMA producer, MMA
+// issuer, idle epilogue warps) so that their polling does not steal issue slots from the warps doing arithmetic.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if (++spins > (SLEEP_NS > 0 ? 20000000u : 400000000u)) {
             printf("camc2v_b200: mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
             __trap();
         }

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                 }
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_wait<100>(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * S::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + S::A_BYTES;
                 mbar_expect_tx(&full_bar[s], tx);
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         for (int it = 0; it < iters; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait<20>(&full_bar[s], ph);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             const bool has_res = p.residual != nullptr && !part;
             const bool out_f32 = part || !p.out_bf16;
             const bool leader = threadIdx.x == 64;      // warp 2, lane 0: owns the bulk async-group of the stores
-            mbar_wait(acc_bar, 0);                      // every MMA has completed: accumulator valid, smem stages free
+            mbar_wait<200>(acc_bar, 0);                 // every MMA has completed: accumulator valid, smem stages free
             tc_fence_after();
             if (leader && has_res) {
                 for (int c = 0; c < NCH; ++c) {
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             if (leader) tma_store_wait_read_all();
             tc_fence_before();
         } else {
-        mbar_wait(acc_bar, 0);
+        mbar_wait<200>(acc_bar, 0);
         tc_fence_after();
         const float* resid = part ? nullptr : p.residual;
         const int out_bf16 = part ? 0 : p.out_bf16;

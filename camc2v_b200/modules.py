@@ -621,7 +621,8 @@ class BasicTransformerBlock(_Prepared):
             wf = self.cc_projection.weight.detach().float()
             p["cc_split"] = (_bf16(wf[:, :C]), _bf16(wf[:, C:]))
         wx, wrt = p["cc_split"]
-        rb = ops.skinny_linear(_f32(cam.RT).view(dm.B * dm.T, -1), _pad_cols(wrt, 16), b, False)   # [B*T, C]
+        rt = _pad_cols(_f32(cam.RT).view(dm.B * dm.T, -1), 16)
+        rb = ops.skinny_linear(rt, _pad_cols(wrt, 16), b, False)                                    # [B*T, C]
         return ops.linear(ops.cast_bf16(x), wx, rowbias=rb, rows_per_group=dm.HW)
 
     # ---- reference signature ----
@@ -996,7 +997,11 @@ class UNetModel(_Prepared):
                 cam = self._camera_level(camera_condition, self.input_ds[i], dm, dev)
                 h, dm = module.forward_cl(h, emb, ctx, dm, cam)
             if i == 0 and self.addition_attention:
-                h, dm = self.init_attn.forward_cl(h, emb, ctx, dm, None)
+                # no camera condition for init_attn (modified_forwards.py:80-81), except MotionCtrl (motionctrl_modified_modules.py:69)
+                cam0 = None
+                if camera_condition is not None and self.init_attn[0].transformer_blocks[0].variant == "motionctrl":
+                    cam0 = self._camera_level(camera_condition, 1, dm, dev)
+                h, dm = self.init_attn.forward_cl(h, emb, ctx, dm, cam0)
             hs.append(h)
         cam = self._camera_level(camera_condition, self.middle_ds, dm, dev, middle=True)
         h, dm = self.middle_block.forward_cl(h, emb, ctx, dm, cam)

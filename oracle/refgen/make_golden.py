@@ -192,6 +192,38 @@ def gen_unet_full(check):
         print(f"    oracle cond pass {time.time() - t0:.1f}s; vs reference rel-L2 {rel_err(y, y_c)[0]:.3e} max-norm {rel_err(y, y_c)[1]:.3e}")
 
 
+def gen_variants(check):
+    """CameraCtrl / MotionCtrl baselines (R/baseline/*): one small-config UNet pass each through the reference's classes."""
+    out = {}
+    for kind in ("cameractrl", "motionctrl"):
+        model = rh.build_baseline_model(kind, unet_overrides=SMALL_UNET)
+        unet = model.model.diffusion_model
+        synth.fill_module_(unet, seed=3)
+        cfg = UNetConfig(model_channels=64, origin_h=128, origin_w=128, variant=kind)
+        inp = synth_inputs(cfg, SMALL_HW, 0, "variant")
+        xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+        t = torch.full((1,), 399, dtype=torch.long)
+        if kind == "cameractrl":
+            cam = {"pluker_embedding_features": inp["pluker"]}
+        else:
+            cam = {"RT": synth.synth_tensor("variant.RT", (1, 16, 12), 5)}
+        with torch.no_grad():
+            y = unet(xc, t, context=inp["ctx_uncond"], fs=inp["fs"], camera_condition=cam)
+        out[f"{kind}.y"] = y.numpy()
+        out[f"{kind}.nkeys"] = np.int64(len(unet.state_dict()))
+        print(f"  {kind}: out std {y.std():.4f}, {len(unet.state_dict())} tensors")
+        if check:
+            from oracle.unet_oracle import UNetOracle
+            yo = UNetOracle(unet.state_dict(), cfg).forward(xc, t, inp["ctx_uncond"], inp["fs"], cam)
+            print(f"    oracle vs reference [{kind}]: rel-L2 {rel_err(yo, y)[0]:.3e} max-norm {rel_err(yo, y)[1]:.3e}")
+            from camc2v_b200.modules import build_unet
+            with torch.device("meta"):
+                mine = {k: tuple(v.shape) for k, v in build_unet(cfg, variant=kind).state_dict().items()}
+            ref = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+            print(f"    state_dict keys/shapes equal to camc2v_b200.modules: {mine == ref}")
+    np.savez_compressed(os.path.join(GOLD, "variants.npz"), **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -205,6 +237,9 @@ if __name__ == "__main__":
     if a.only in (None, "unet_small", "ddim"):
         print("[unet_small + ddim step]")
         gen_unet_small(a.check_oracle)
+    if a.only in (None, "variants"):
+        print("[variants]")
+        gen_variants(a.check_oracle)
     if a.only in ("unet_full",):
         print("[unet_full]")
         gen_unet_full(a.check_oracle)

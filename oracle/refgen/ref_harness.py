@@ -146,6 +146,32 @@ def build_reference_model(unet_overrides: dict | None = None, seed: int = 0):
     return model
 
 
+def build_baseline_model(kind: str, unet_overrides: dict | None = None, seed: int = 0):
+    """Construct one of the reference's baselines (R/baseline/*): 'cameractrl', 'motionctrl', 'cami2v'."""
+    setup_reference_imports()
+    import importlib
+    target, cfgname = {
+        "cameractrl": ("baseline.cameractrl.cameractrl.CameraCtrl", "baseline/cameractrl_256.yaml"),
+        "motionctrl": ("baseline.motionctrl.motionctrl.MotionCtrl", "baseline/motionctrl_256.yaml"),
+        "cami2v": ("baseline.cami2v.cami2v.CamI2V", "baseline/cami2v_256.yaml"),
+    }[kind]
+    mc = load_model_config(cfgname)
+    p = mc.params
+    for k in ("first_stage_config", "cond_stage_config", "img_cond_stage_config", "image_proj_stage_config"):
+        p[k] = to_attr(IDENTITY)
+    if "pose_encoder_config" in p:
+        p.pose_encoder_config = None
+    if unet_overrides:
+        for k, v in unet_overrides.items():
+            p.unet_config.params[k] = v
+    mod, cls = target.rsplit(".", 1)
+    klass = getattr(importlib.import_module(mod), cls)
+    torch.manual_seed(seed)
+    model = klass(**p)
+    model.eval()
+    return model
+
+
 def patch_ddim_for_cpu():
     setup_reference_imports()
     from lvdm.models.samplers.ddim import DDIMSampler

@@ -161,3 +161,23 @@ def test_fused_epipolar_oracle_equals_explicit(small):
     a = fast.forward(xc, t, inp["ctx_cond"], inp["fs"], cam, max_input_block=2)
     b = orc.forward(xc, t, inp["ctx_cond"], inp["fs"], cam, max_input_block=2)
     assert _rel(a, b)[0] < 1e-5
+
+
+@pytest.mark.parametrize("variant", ["cameractrl", "motionctrl"])
+def test_variant_oracles_match_reference_baselines(variant):
+    """CameraCtrl / MotionCtrl blocks (R/baseline/*) — BASELINE.json configs[4]."""
+    from camc2v_b200.modules import build_unet
+    from oracle.unet_oracle import UNetOracle
+    cfg = UNetConfig(model_channels=64, origin_h=128, origin_w=128, variant=variant)
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in build_unet(cfg, variant=variant).state_dict().items()}
+    g = np.load(os.path.join(GOLD, "variants.npz"))
+    assert len(shapes) == int(g[f"{variant}.nkeys"])
+    sd = synth.synth_state_dict(shapes, 3)
+    inp = synth_unet_inputs(cfg, 16, 0, "variant")
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    t = torch.full((1,), 399, dtype=torch.long)
+    cam = {"pluker_embedding_features": inp["pluker"]} if variant == "cameractrl" else {"RT": synth.synth_tensor("variant.RT", (1, 16, 12), 5)}
+    y = UNetOracle(sd, cfg).forward(xc, t, inp["ctx_uncond"], inp["fs"], cam)
+    l2, mx = _rel(y, torch.from_numpy(g[f"{variant}.y"]))
+    assert l2 < 1e-5 and mx < 1e-5, (l2, mx)

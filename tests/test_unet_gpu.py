@@ -148,6 +148,41 @@ def test_module_forwards_reference_layout_vs_oracle(small):
     assert rel(y, y_ref)[0] < 1e-2
 
 
+@pytest.mark.parametrize("variant", ["cameractrl", "motionctrl", "none"])
+def test_baseline_variants_vs_oracle(variant):
+    """CameraCtrl / MotionCtrl conditioning blocks (BASELINE config 5) through the same kernels, against the
+    CPU oracle's restatement of R/baseline/*/..._modified_modules.py on the same synthetic weights and inputs."""
+    from camc2v_b200 import synth
+    from camc2v_b200.config import UNetConfig
+    from camc2v_b200.modules import build_unet
+    from camc2v_b200.testing import synth_unet_inputs
+    from oracle.unet_oracle import UNetOracle
+    cfg = UNetConfig(model_channels=64, origin_h=128, origin_w=128, variant=variant)
+    unet = build_unet(cfg, variant=variant)
+    synth.fill_module_(unet, seed=3)
+    sd = {k: v.clone() for k, v in unet.state_dict().items()}
+    unet = unet.to(DEV)
+    inp = synth_unet_inputs(cfg, 16, 0, "variant")
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    t = torch.full((1,), 399, dtype=torch.long)
+    if variant == "cameractrl":
+        cam_o = {"pluker_embedding_features": inp["pluker"]}
+        cam_d = {"pluker_embedding_features": [p.to(DEV) for p in inp["pluker"]]}
+    elif variant == "motionctrl":
+        rt = synth.synth_tensor("variant.RT", (1, 16, 12), 5)
+        cam_o, cam_d = {"RT": rt}, {"RT": rt.to(DEV)}
+    else:
+        cam_o = cam_d = None
+    y_ref = UNetOracle(sd, cfg).forward(xc, t, inp["ctx_uncond"], inp["fs"], cam_o)
+    y = unet(xc.to(DEV), t.to(DEV), context=inp["ctx_uncond"].to(DEV), fs=inp["fs"].to(DEV), camera_condition=cam_d)
+    l2, mx = rel(y, y_ref)
+    assert l2 < TOL_L2 and mx < TOL_MAX, (variant, l2, mx)
+    if variant != "none":      # and against the golden output of the reference's own baseline class
+        g = np.load(os.path.join(GOLD, "variants.npz"))
+        l2, mx = rel(y, torch.from_numpy(g[f"{variant}.y"]))
+        assert l2 < TOL_L2 and mx < TOL_MAX, (variant, l2, mx)
+
+
 def test_unsupported_configurations_raise():
     from camc2v_b200.modules import UNetModel
     with pytest.raises(NotImplementedError):
