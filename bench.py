@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=1, help="videos per GPU")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--serial-passes", action="store_true", help="do not overlap the cond / uncond UNet passes inside the CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -318,6 +319,7 @@ def main():
     for k in ("x", "c_concat", "ctx_cond", "ctx_uncond"):
         host[k] = pin(host[k])
     host["pluker"] = [pin(p) for p in host["pluker"]]
+    sampler.concurrent_passes = not args.serial_passes
     cond, uc, static, cond_bytes = to_device_conditioning(host, cam_host, device)
     kw = dict(unconditional_guidance_scale=3.5, unconditional_conditioning=uc, guidance_rescale=0.7, fs=static["fs"],
               enable_camera_condition=True, use_cuda_graph=not args.no_graph)

@@ -202,10 +202,10 @@ int c2v_groupnorm_silu(const float* x, const float* gamma, const float* beta, vo
 
 int64_t c2v_groupnorm_ws_floats(int ns, int rows, int C) { return groupnorm_ws_floats(ns, rows, C); }
 
-int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, int rows, int C, float eps,
-                  void* stream) {
+int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32, int rows,
+                  int C, float eps, void* stream) {
     if (!x || !gamma || !beta || !out) return ERR_BAD_ARG;
-    return layernorm_launch(x, gamma, beta, out, add, out2, rows, C, eps, (cudaStream_t)stream);
+    return layernorm_launch(x, gamma, beta, out, add, out2, out_f32, rows, C, eps, (cudaStream_t)stream);
 }
 
 int c2v_attention(const c2v_attn_desc* d, void* stream) {

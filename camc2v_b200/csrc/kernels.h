@@ -9,8 +9,8 @@ namespace c2v {
 int64_t groupnorm_ws_floats(int ns, int rows, int C);
 int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps,
                           int silu, cudaStream_t st);
-int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, int rows, int C,
-                     float eps, cudaStream_t st);
+int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32,
+                     int rows, int C, float eps, cudaStream_t st);
 
 // elementwise.cu
 int to_channels_last_launch(const float* in, void* out, int B, int C, int S, int Cpad, int out_bf16, cudaStream_t st);

@@ -110,13 +110,26 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_apply_kernel(const float* __
                                                               __nv_bfloat16* __restrict__ out, int rows, int C, int rows_per_slab,
                                                               float eps, int silu) {
     __shared__ float s_mean[32], s_rstd[32];
+    __shared__ double s_ps[16][32], s_pq[16][32];
     const int n = blockIdx.y, slab = blockIdx.x, nslab = gridDim.x;
-    if (threadIdx.x < 32) {
+    {   // reduce the per-slab partials: 16 threads per group in parallel, then a fixed-order sum (deterministic)
+        const int g = threadIdx.x & 31, part = threadIdx.x >> 5;       // 512 threads = 16 parts x 32 groups
         double s = 0.0, q = 0.0;
-        const float* w = ws + ((size_t)n * nslab * 32 + threadIdx.x) * 2;
-        for (int i = 0; i < nslab; ++i) {
+        const float* w = ws + ((size_t)n * nslab * 32 + g) * 2;
+        for (int i = part; i < nslab; i += 16) {
             s += (double)w[(size_t)i * 64];
             q += (double)w[(size_t)i * 64 + 1];
+        }
+        s_ps[part][g] = s;
+        s_pq[part][g] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0, q = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            s += s_ps[i][threadIdx.x];
+            q += s_pq[i][threadIdx.x];
         }
         const double cnt = (double)rows * (double)(C / 32);
         const double mean = s / cnt;
@@ -203,8 +216,8 @@ constexpr int LN_MAXV = 10;   // float4 per lane -> C <= 1280
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
-                                                        const float* __restrict__ add, __nv_bfloat16* __restrict__ out2, int rows, int C,
-                                                        float eps) {
+                                                        const float* __restrict__ add, __nv_bfloat16* __restrict__ out2,
+                                                        float* __restrict__ out_f32, int rows, int C, float eps) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -242,6 +255,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             const float y2 = (v[i].z - mean) * rstd * g.z + bb.z;
             const float y3 = (v[i].w - mean) * rstd * g.w + bb.w;
             *reinterpret_cast<uint2*>(out + (size_t)row * C + cv * 4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * C + cv * 4) = make_float4(y0, y1, y2, y3);
             if (add) {
                 const float4 p = *reinterpret_cast<const float4*>(add + (size_t)row * C + cv * 4);
                 *reinterpret_cast<uint2*>(out2 + (size_t)row * C + cv * 4) =
@@ -251,13 +265,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
-int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, int rows, int C,
-                     float eps, cudaStream_t st) {
+int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32,
+                     int rows, int C, float eps, cudaStream_t st) {
     if (C % 4 != 0 || (C >> 2) > LN_MAXV * 32 || rows <= 0) return ERR_UNSUPPORTED;
     if (add && !out2) return ERR_BAD_ARG;
     const int wpb = 8;
     layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), add,
-                                                                 reinterpret_cast<__nv_bfloat16*>(out2), rows, C, eps);
+                                                                 reinterpret_cast<__nv_bfloat16*>(out2), out_f32, rows, C, eps);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -601,9 +601,9 @@ class BasicTransformerBlock(_Prepared):
             if has_epi:
                 x = self.epipolar.epipolar_attn.forward_cl(src, dm, cam, residual=x)   # + Epipolar(n + p)
         elif cam is not None and self.variant == "cameractrl" and "cc_projection" in p and cam.pluker is not None:
-            n, src = ops.layernorm(x, p["g1"], p["b1"], add=cam.pluker)
+            n, src, nf = ops.layernorm(x, p["g1"], p["b1"], add=cam.pluker, want_f32=True)
             w, b = p["cc_projection"]
-            n2 = ops.linear(src, w, bias=b, residual=n.float(), out_dtype=BF16)     # n + cc_projection(n + p)
+            n2 = ops.linear(src, w, bias=b, residual=nf, out_dtype=BF16)            # n + cc_projection(n + p)
             x = self.attn1.self_temporal(n2, dm, residual=x)
         else:
             x = self.attn1.self_temporal(ops.layernorm(x, p["g1"], p["b1"]), dm, residual=x)

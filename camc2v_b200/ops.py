@@ -130,13 +130,16 @@ def groupnorm(x: torch.Tensor, gamma, beta, ns: int, rows: int, eps: float, silu
     return out
 
 
-def layernorm(x: torch.Tensor, gamma, beta, add: Optional[torch.Tensor] = None, eps: float = 1e-5):
+def layernorm(x: torch.Tensor, gamma, beta, add: Optional[torch.Tensor] = None, eps: float = 1e-5, want_f32: bool = False):
+    """Returns LN(x) in bf16; with `add` also LN(x)+add (bf16); with want_f32 also the un-rounded fp32 LN(x) (last)."""
     _chk(x, F32, "layernorm.x")
     rows, C_ = x.shape
     out = torch.empty((rows, C_), device=x.device, dtype=BF16)
     out2 = torch.empty_like(out) if add is not None else None
-    _lib.call("c2v_layernorm", _p(x), _p(gamma), _p(beta), _p(out), _p(add), _p(out2), rows, C_, float(eps), _stream())
-    return (out, out2) if add is not None else out
+    of = torch.empty((rows, C_), device=x.device, dtype=F32) if want_f32 else None
+    _lib.call("c2v_layernorm", _p(x), _p(gamma), _p(beta), _p(out), _p(add), _p(out2), _p(of), rows, C_, float(eps), _stream())
+    res = (out,) + ((out2,) if add is not None else ()) + ((of,) if want_f32 else ())
+    return res if len(res) > 1 else out
 
 
 # ------------------------------------------------------------------------------------------------ attention

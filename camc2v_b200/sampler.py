@@ -90,6 +90,7 @@ class DDIMSampler(object):
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
         self._graph = None
+        self.concurrent_passes = kwargs.get("concurrent_passes", True)
 
     # -------------------------------------------------------------------------------------------- schedule
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
@@ -165,8 +166,19 @@ class DDIMSampler(object):
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                ec = self.model.apply_model(sx, st, c, **kwargs)
-                eu = self.model.apply_model(sx, st, uc, **kwargs)
+                # The cond and uncond passes are independent: capture them as two parallel branches of the graph so that
+                # the small grids of the 8x8 / 4x4 levels and every kernel's last partial wave overlap with the other pass.
+                main = torch.cuda.current_stream()
+                if self.concurrent_passes:
+                    side2 = torch.cuda.Stream()
+                    side2.wait_stream(main)
+                    ec = self.model.apply_model(sx, st, c, **kwargs)
+                    with torch.cuda.stream(side2):
+                        eu = self.model.apply_model(sx, st, uc, **kwargs)
+                    main.wait_stream(side2)
+                else:
+                    ec = self.model.apply_model(sx, st, c, **kwargs)
+                    eu = self.model.apply_model(sx, st, uc, **kwargs)
             g = self._graph = dict(key=key, graph=graph, x=sx, t=st, ec=ec, eu=eu)
         g["x"].copy_(x)
         g["t"].copy_(t)

@@ -87,9 +87,10 @@ int64_t c2v_groupnorm_ws_floats(int ns, int rows, int C);
 
 /* LayerNorm over the last dim (nn.LayerNorm, attention.py:232-234), fp32 in -> bf16 out.  If `add` is not
  * NULL a second output out2 = LN(x) + add is produced (normed_x + pluker features,
- * R/model/modules/modified_forwards.py:508-520); add is fp32 [rows, C]. */
+ * R/model/modules/modified_forwards.py:508-520); add is fp32 [rows, C].  out_f32 (optional) receives the
+ * un-rounded normalised rows (CameraCtrl adds cc_projection(...) to them, cameractrl_modified_modules.py:235-239). */
 int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, const float* add, void* out2_bf16,
-                  int rows, int C, float eps, void* stream);
+                  float* out_f32, int rows, int C, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention.
