@@ -208,6 +208,8 @@ int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* o
     return layernorm_launch(x, gamma, beta, out, add, out2, out_f32, rows, C, eps, (cudaStream_t)stream);
 }
 
+int c2v_epipolar_tile_map_words(int T, int H, int W);
+
 int c2v_attention(const c2v_attn_desc* d, void* stream) {
     if (!d || !d->q || !d->k || !d->v || !d->out) return ERR_BAD_ARG;
     if (d->bq <= 0 || d->lq <= 0 || d->lk <= 0 || d->heads <= 0 || d->kv_div <= 0) return ERR_BAD_ARG;
@@ -262,6 +264,10 @@ int c2v_attention(const c2v_attn_desc* d, void* stream) {
     }
     a.mask = d->mask;
     a.mask_bstride = d->mask_bstride;
+    if (d->epi_tile_map && d->epi_F) {
+        a.tile_map = d->epi_tile_map;
+        a.tile_map_words = c2v_epipolar_tile_map_words(d->epi_T, d->epi_H, d->epi_W);
+    }
     return attn_tc_launch(a, (d->lq + 127) / 128, d->heads, d->bq, (cudaStream_t)stream);
 }
 
@@ -273,6 +279,13 @@ int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int
 int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, int d, void* stream) {
     if (!F || !out) return ERR_BAD_ARG;
     return epipolar_mask_launch(F, out, B, T, H, W, d, (cudaStream_t)stream);
+}
+
+int c2v_epipolar_tile_map_words(int T, int H, int W) { return ((T * H * W + 127) / 128 + 31) / 32; }
+
+int c2v_epipolar_tile_map(const float* F, uint32_t* map, int B, int T, int H, int W, int d, void* stream) {
+    if (!F || !map || B <= 0 || B > 65535) return ERR_BAD_ARG;
+    return epi_tile_map_launch(F, map, B, T, H, W, d, (cudaStream_t)stream);
 }
 
 int c2v_plucker(const float* K, const float* c2w, float* out, int B, int T, int H, int W, int plucker, void* stream) {

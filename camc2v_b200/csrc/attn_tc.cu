@@ -35,7 +35,9 @@ constexpr int AT_OFF_K = AT_OFF_Q + AT_Q_BYTES;
 constexpr int AT_OFF_V = AT_OFF_K + AT_KV_STAGES * AT_K_BYTES;
 constexpr int AT_OFF_P = AT_OFF_V + AT_KV_STAGES * AT_V_BYTES;
 constexpr int AT_OFF_BAR = AT_OFF_P + AT_P_BYTES;
-constexpr int AT_SMEM = AT_OFF_BAR + 128;
+constexpr int AT_OFF_LIST = AT_OFF_BAR + 128;                   // active key-tile list (uint16), <= AT_MAX_TILES entries
+constexpr int AT_MAX_TILES = 384;
+constexpr int AT_SMEM = AT_OFF_LIST + AT_MAX_TILES * 2;
 
 constexpr uint32_t AT_TMEM_COLS = 256;
 constexpr uint32_t AT_TM_S = 0;       // S accumulator: columns [0,128)
@@ -109,19 +111,39 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         tmem_alloc(tmem_ptr, AT_TMEM_COLS);
         tmem_relinquish();
     }
+    // Key tiles this query tile has to visit.  With an epipolar tile map (one bit per (query tile, key tile), built once per
+    // sample by epi_tile_map_kernel with the same conservative test as the in-tile row skip) tiles that cannot contain an
+    // unmasked pair are never loaded, multiplied or soft-maxed.
+    uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + AT_OFF_LIST);
+    int* n_act_s = reinterpret_cast<int*>(bars + 10);
+    if (warp == 2) {
+        const uint32_t* map = p.tile_map ? p.tile_map + ((size_t)b * gridDim.x + blockIdx.x) * p.tile_map_words : nullptr;
+        int cnt = 0;
+        for (int j0 = 0; j0 < n_tiles; j0 += 32) {
+            const int j = j0 + lane_id();
+            bool act = j < n_tiles;
+            if (act && map && j < n_main) act = (map[j >> 5] >> (j & 31)) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, act);
+            if (act) tile_list[cnt + __popc(bal & ((1u << lane_id()) - 1u))] = (uint16_t)j;
+            cnt += __popc(bal);
+        }
+        if (lane_id() == 0) *n_act_s = cnt;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const int n_act = *n_act_s;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             mbar_expect_tx(q_full, AT_Q_BYTES);
             tma_load_3d(smem + AT_OFF_Q, &p.tmQ, q_full, head * AT_D, q0, b);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j % AT_KV_STAGES;
-                const uint32_t ph = (j / AT_KV_STAGES) & 1;
+            for (int it = 0; it < n_act; ++it) {
+                const int j = tile_list[it];
+                const int s = it % AT_KV_STAGES;
+                const uint32_t ph = (it / AT_KV_STAGES) & 1;
                 mbar_wait<200>(&kv_empty[s], ph ^ 1);
                 mbar_expect_tx(&kv_full[s], AT_K_BYTES + AT_V_BYTES);
                 if (j < n_main) {
@@ -139,7 +161,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, AT_D, 0, 1);   // B = V is MN-major
         const uint32_t q_addr = smem_u32(smem + AT_OFF_Q);
         const uint32_t p_addr = smem_u32(smem + AT_OFF_P);
-        auto issue_qk = [&](int j) {
+        auto issue_qk = [&](int j) {                  // j = iteration index over the active-tile list
             const int s = j % AT_KV_STAGES;
             mbar_wait<40>(&kv_full[s], (j / AT_KV_STAGES) & 1);
             if (j > 0) mbar_wait<40>(s_free, (j - 1) & 1);
@@ -155,9 +177,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         };
         mbar_wait<40>(q_full, 0);
         issue_qk(0);
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = 0; j < n_act; ++j) {
             const int s = j % AT_KV_STAGES;
-            if (j + 1 < n_tiles) issue_qk(j + 1);     // overlaps with the softmax warps writing P(j)
+            if (j + 1 < n_act) issue_qk(j + 1);       // overlaps with the softmax warps writing P(j)
             mbar_wait<40>(p_full, j & 1);
             tc_fence_after();
             if (elect_one()) {
@@ -201,15 +223,16 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         float l_run = 0.f;
         uint8_t* p_row = smem + AT_OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
 
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = 0; j < n_act; ++j) {
+            const int jt = tile_list[j];              // key tile index (j counts visited tiles: barrier parities)
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             uint32_t bits[4];
             uint32_t anyc = 0;       // chunks in which at least one lane of this warp has a valid key (warp-uniform)
             float mx = -INFINITY;
-            const bool main_seg = j < n_main;
+            const bool main_seg = jt < n_main;
             const int klim = main_seg ? p.lk : p.lk2;
-            const int tile_key0 = main_seg ? j * AT_BN : 0;
+            const int tile_key0 = main_seg ? jt * AT_BN : 0;
             // ---- pass 1: validity mask + row max ----
             if (FAST && epi && main_seg) {
                 // Square power-of-two key grid: a 32-key chunk is RPC whole image rows of one frame, pixel x of column i
@@ -379,9 +402,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             mbar_arrive(p_full);
         }
         // ---- epilogue: O / l -> bf16 -> global ----
-        mbar_wait(pv_done, (n_tiles - 1) & 1);
+        if (n_act > 0) mbar_wait(pv_done, (n_act - 1) & 1);
         tc_fence_after();
-        const float inv = (l_run > 0.f) ? p.out_scale / l_run : 0.f;
+        const float inv = (l_run > 0.f && n_act > 0) ? p.out_scale / l_run : 0.f;
         const bool row_ok = qi < p.lq;
         __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)b * p.o_bstride + (size_t)qi * p.ldo + head * AT_D;
 #pragma unroll
@@ -394,7 +417,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                 for (int i = 0; i < 32; i += 8) {
                     float f[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[i + e]) * inv;
+                    for (int e = 0; e < 8; ++e) f[e] = inv != 0.f ? __uint_as_float(o[i + e]) * inv : 0.f;
                     uint4* dst = reinterpret_cast<uint4*>(orow + c * 32 + i);
                     if (p.accumulate) {
                         const uint4 prev = *dst;
@@ -418,6 +441,74 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epipolar tile map: bit (q_tile, k_tile) = "some query of the 128-query tile may see some key of the 128-key tile".
+// Same conservative per-image-row interval test (and the same rounding margin) as the in-tile row skip of attn_tc_kernel,
+// so a cleared bit implies every chunk of that tile would have been skipped anyway: results are bit-identical with and
+// without the map.  F is constant over the 25 steps x 2 passes x 16 layers of a sample, so the map is built once per sample.
+// ------------------------------------------------------------------------------------------------
+template <int LOGW, int D>
+__global__ void __launch_bounds__(128) epi_tile_map_kernel(const float* __restrict__ Fm, unsigned int* __restrict__ map, int T, int n_ktiles,
+                                                           int words, float thr) {
+    constexpr int W = 1 << LOGW, HW = W * W;
+    constexpr float DF = (float)D, OFFC = (float)D * 0.5f - 0.5f;
+    const int b = blockIdx.y, qt = blockIdx.x;
+    const int L = T * HW;
+    const int qi = min(qt * AT_BM + (int)threadIdx.x, L - 1);
+    const int t1 = qi >> (2 * LOGW), pix = qi & (HW - 1);
+    const float xi = (float)(pix & (W - 1)) * DF + OFFC, yi = (float)(pix >> LOGW) * DF + OFFC;
+    const float* Frow = Fm + ((size_t)b * T + t1) * T * 9;
+    unsigned int* out = map + ((size_t)b * gridDim.x + qt) * words;
+    int cur_t2 = -1;
+    EpiLine line = {0.f, 0.f, 0.f};
+    float thr_m = 0.f;
+    unsigned int word = 0;
+    for (int j = 0; j < n_ktiles; ++j) {
+        bool maybe = false;
+        for (int rr = 0; rr < AT_BN / W; ++rr) {
+            const int key0 = j * AT_BN + rr * W;
+            if (key0 >= L) break;
+            const int t2 = key0 >> (2 * LOGW);
+            if (t2 != cur_t2) {
+                cur_t2 = t2;
+                line = epi_line(Frow + t2 * 9, xi, yi);
+                const float cmax = (float)(W - 1) * DF + OFFC;
+                thr_m = thr + 1e-6f + 4e-7f * (fabsf(line.l0) * cmax + fabsf(line.l1) * cmax + fabsf(line.l2));
+            }
+            const float yr = (float)((key0 & (HW - 1)) >> LOGW) * DF + OFFC;
+            const float w0 = __fadd_rn(__fmaf_rn(line.l1, yr, __fmul_rn(line.l0, OFFC)), line.l2);
+            const float w1 = __fadd_rn(__fmaf_rn(line.l1, yr, __fmul_rn(line.l0, (float)(W - 1) * DF + OFFC)), line.l2);
+            maybe |= !((w0 > thr_m && w1 > thr_m) || (w0 < -thr_m && w1 < -thr_m));
+        }
+        const int any = __syncthreads_or(maybe ? 1 : 0);
+        if (threadIdx.x == 0) {
+            if (any) word |= 1u << (j & 31);
+            if ((j & 31) == 31 || j == n_ktiles - 1) {
+                out[j >> 5] = word;
+                word = 0;
+            }
+        }
+    }
+}
+
+int epi_tile_map_launch(const float* F, unsigned int* map, int B, int T, int H, int W, int d, cudaStream_t st) {
+    if (H != W) return ERR_UNSUPPORTED;
+    const int L = T * H * W;
+    const int nq = (L + AT_BM - 1) / AT_BM, nk = (L + AT_BN - 1) / AT_BN, words = (nk + 31) / 32;
+    const float thr = (float)((double)d * sqrt(2.0) / 2.0);
+    dim3 grid(nq, B);
+#define C2V_MAP(LW, DD) epi_tile_map_kernel<LW, DD><<<grid, 128, 0, st>>>(F, map, T, nk, words, thr)
+    if (W == 32 && d == 8) C2V_MAP(5, 8);
+    else if (W == 16 && d == 16) C2V_MAP(4, 16);
+    else if (W == 8 && d == 32) C2V_MAP(3, 32);
+    else if (W == 16 && d == 8) C2V_MAP(4, 8);
+    else if (W == 8 && d == 16) C2V_MAP(3, 16);
+    else return ERR_UNSUPPORTED;
+#undef C2V_MAP
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
 template <int LOGW, int D>
 static int launch_attn(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
     static bool attr_set = false;
@@ -439,7 +530,9 @@ int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, c
         if (w == 16 && d == 8) return launch_attn<4, 8>(a, q_tiles, heads, batch, st);
         if (w == 8 && d == 16) return launch_attn<3, 16>(a, q_tiles, heads, batch, st);
     }
-    return launch_attn<0, 1>(a, q_tiles, heads, batch, st);
+    AttnKernelArgs g = a;
+    g.tile_map = nullptr;                     // the tile map is defined for the power-of-two grids only
+    return launch_attn<0, 1>(g, q_tiles, heads, batch, st);
 }
 
 }  // namespace c2v

@@ -480,7 +480,7 @@ class EpipolarCrossAttention(_Prepared):
             k2, v2 = p["kv_reg"][:, :C], p["kv_reg"][:, C:]
         kw = {}
         if cam.F is not None:
-            kw = dict(epi_F=cam.F, epi_grid=(dm.T, dm.H, dm.W), epi_d=cam.d)
+            kw = dict(epi_F=cam.F, epi_grid=(dm.T, dm.H, dm.W), epi_d=cam.d, epi_tile_map=_tile_map(cam.F, dm.T, dm.H, dm.W, cam.d))
         elif cam.mask is not None:
             kw = dict(mask=cam.mask)
         o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], dm.B, L, L, self.heads, k2=k2, v2=v2, **kw)
@@ -658,20 +658,53 @@ def _pad_cols(w: torch.Tensor, mult: int):
     return torch.cat([w, w.new_zeros(w.shape[0], mult - k % mult)], dim=1).contiguous()
 
 
-_PLUKER_CACHE: Dict[tuple, torch.Tensor] = {}
+# Derived camera state, cached per source tensor (address + shape).  Both are functions of per-sample constants (F, Pluecker
+# features) that do not change over the 25 steps x 2 passes of a sample.  An entry whose source tensor was modified in place
+# (torch bumps `_version`) is recomputed INTO THE SAME BUFFER, so pointers captured in a CUDA graph stay valid; callers that
+# replay a graph after refilling static conditioning buffers call `refresh_camera_caches()` first.
+_PLUKER_CACHE: Dict[tuple, list] = {}
+_TILEMAP_CACHE: Dict[tuple, list] = {}
+
+
+def _tile_map(Fm: torch.Tensor, T: int, H: int, W: int, d: int):
+    """Tile-occupancy bitmap of the epipolar mask: a function of F only, so it is built once per sample and level."""
+    key = (Fm.data_ptr(), tuple(Fm.shape), T, H, W, d)
+    ent = _TILEMAP_CACHE.get(key)
+    if ent is None:
+        if len(_TILEMAP_CACHE) > 64:
+            _TILEMAP_CACHE.clear()
+        ent = _TILEMAP_CACHE[key] = [Fm._version, ops.epipolar_tile_map(Fm, T, H, W, d), Fm]
+    elif ent[0] != Fm._version:
+        ent[0] = Fm._version
+        if ent[1] is not None:
+            ops.epipolar_tile_map(Fm, T, H, W, d, out=ent[1])
+    return ent[1]
 
 
 def _pluker_cl(p: torch.Tensor) -> torch.Tensor:
     """[B, C, T, h, w] fp32 -> CL fp32 [B*T*hw, C]; constant over the 25 steps x 2 CFG passes, so cached."""
-    key = (p.data_ptr(), p._version, tuple(p.shape), str(p.device))
-    hit = _PLUKER_CACHE.get(key)
-    if hit is None:
+    key = (p.data_ptr(), tuple(p.shape), str(p.device))
+    B, C, T, h, w = p.shape
+    ent = _PLUKER_CACHE.get(key)
+    if ent is None:
         if len(_PLUKER_CACHE) > 64:
             _PLUKER_CACHE.clear()
-        B, C, T, h, w = p.shape
-        hit = ops.to_channels_last(_f32(p), B, C, T * h * w)
-        _PLUKER_CACHE[key] = hit
-    return hit
+        ent = _PLUKER_CACHE[key] = [p._version, ops.to_channels_last(_f32(p), B, C, T * h * w), p]
+    elif ent[0] != p._version:
+        ent[0] = p._version
+        ops.to_channels_last(_f32(p), B, C, T * h * w, out=ent[1])
+    return ent[1]
+
+
+def refresh_camera_caches() -> None:
+    """Re-derive (in place) every cached tile map / channels-last Pluecker copy whose source tensor was refilled."""
+    for key, ent in list(_TILEMAP_CACHE.items()):
+        Fm = ent[2]
+        if ent[0] != Fm._version:
+            _tile_map(Fm, *key[2:])
+    for ent in list(_PLUKER_CACHE.values()):
+        if ent[0] != ent[2]._version:
+            _pluker_cl(ent[2])
 
 
 def camera_level_from_condition(cc: dict, B: int, T: int, H: int, W: int, device, origin_h: int = 256) -> CameraLevel:

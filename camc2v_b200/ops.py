@@ -144,7 +144,7 @@ def layernorm(x: torch.Tensor, gamma, beta, add: Optional[torch.Tensor] = None, 
 
 # ------------------------------------------------------------------------------------------------ attention
 def attention(q, k, v, bq: int, lq: int, lk: int, heads: int, kv_div: int = 1, out=None, out_scale: float = 1.0, accumulate: bool = False,
-              k2=None, v2=None, epi_F=None, epi_grid=None, epi_d: int = 0, mask=None):
+              k2=None, v2=None, epi_F=None, epi_grid=None, epi_d: int = 0, mask=None, epi_tile_map=None):
     """q [bq*lq, >=heads*64] bf16 (row-strided view allowed), k/v [bk*lk, ...]; returns bf16 [bq*lq, heads*64]."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, BF16, "attention." + n)
@@ -165,6 +165,8 @@ def attention(q, k, v, bq: int, lq: int, lk: int, heads: int, kv_div: int = 1, o
         _chk(epi_F, F32, "attention.epi_F")
         T, H, W = epi_grid
         d.epi_F, d.epi_T, d.epi_H, d.epi_W, d.epi_d = _p(epi_F), T, H, W, epi_d
+        if epi_tile_map is not None:
+            d.epi_tile_map = _p(epi_tile_map)
     if mask is not None:
         if mask.dtype not in (torch.bool, torch.uint8) or not mask.is_contiguous():
             raise _lib.C2VError("attention.mask must be contiguous bool/uint8 [bq, lq, lk]")
@@ -193,6 +195,20 @@ def epipolar_mask(F: torch.Tensor, H: int, W: int, d: int) -> torch.Tensor:
     return out.view(torch.bool)
 
 
+def epipolar_tile_map(F: torch.Tensor, T: int, H: int, W: int, d: int, out=None):
+    """Tile-occupancy bitmap for attention(..., epi_F=F, epi_tile_map=...); None when the grid has no fast path."""
+    _chk(F, F32, "epipolar_tile_map.F")
+    if H != W or (W, d) not in ((32, 8), (16, 16), (8, 32), (16, 8), (8, 16)):
+        return None
+    B = F.shape[0]
+    L = T * H * W
+    words = _lib.load().c2v_epipolar_tile_map_words(T, H, W)
+    if out is None:
+        out = torch.empty((B, (L + 127) // 128, words), device=F.device, dtype=torch.int32)
+    _lib.call("c2v_epipolar_tile_map", _p(F.contiguous()), _p(out), B, T, H, W, d, _stream())
+    return out
+
+
 def plucker(K: torch.Tensor, c2w: torch.Tensor, H: int, W: int, mode: str = "plucker") -> torch.Tensor:
     K = K.contiguous().float()
     c2w = c2w.contiguous().float()
@@ -203,11 +219,12 @@ def plucker(K: torch.Tensor, c2w: torch.Tensor, H: int, W: int, mode: str = "plu
 
 
 # ------------------------------------------------------------------------------------------------ layout / glue
-def to_channels_last(x: torch.Tensor, B: int, C_: int, S: int, Cpad: Optional[int] = None, dtype=F32):
+def to_channels_last(x: torch.Tensor, B: int, C_: int, S: int, Cpad: Optional[int] = None, dtype=F32, out=None):
     """x fp32 contiguous, viewed as [B, C, S] -> [B*S, Cpad]."""
     _chk(x, F32, "to_channels_last.x")
     Cpad = Cpad or C_
-    out = torch.empty((B * S, Cpad), device=x.device, dtype=dtype)
+    if out is None:
+        out = torch.empty((B * S, Cpad), device=x.device, dtype=dtype)
     _lib.call("c2v_to_channels_last", _p(x), _p(out), B, C_, S, Cpad, 1 if dtype == BF16 else 0, _stream())
     return out
 

@@ -120,6 +120,8 @@ typedef struct c2v_attn_desc {
     const void* k2; const void* v2; int lk2, ldk2, ldv2;
     const float* epi_F; int epi_T, epi_H, epi_W, epi_d;
     const uint8_t* mask; int64_t mask_bstride;
+    const uint32_t* epi_tile_map;  /* optional (with epi_F): output of c2v_epipolar_tile_map for the same F and grid; key tiles that
+                                      cannot hold an unmasked pair are skipped entirely (results are bit-identical without it) */
 } c2v_attn_desc;
 int c2v_attention(const c2v_attn_desc* d, void* stream);
 
@@ -132,6 +134,11 @@ int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int
  * ---------------------------------------------------------------------------------------------- */
 /* Materialise the epipolar mask (camcontexti2v.py:202-271): F fp32 [B,T,T,3,3] -> uint8 [B, T*H*W, T*H*W]. Bit-exact. */
 int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, int d, void* stream);
+/* Conservative tile-occupancy bitmap of the epipolar mask for 128x128 (query, key) tiles of a square power-of-two grid
+ * (W in {8,16,32}): map[b][q_tile][word] bit j = key tile j may contain an attended pair.  Words per row =
+ * c2v_epipolar_tile_map_words(T,H,W).  Returns 4 (unsupported) for other grids: callers then simply pass no map. */
+int c2v_epipolar_tile_map(const float* F, uint32_t* map, int B, int T, int H, int W, int d, void* stream);
+int c2v_epipolar_tile_map_words(int T, int H, int W);
 /* Pluecker / ray embedding (R/model/base.py:112-174): K fp32 [B,T,3,3], c2w fp32 [B,T,4,4] -> fp32 [B,6,T,H,W]. */
 int c2v_plucker(const float* K, const float* c2w, float* out, int B, int T, int H, int W, int plucker, void* stream);
 

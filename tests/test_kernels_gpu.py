@@ -225,6 +225,19 @@ def test_attention_epipolar(T, H, W, d, heads, kind):
     out_m = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], mask=mask.contiguous())
     close(out_m, ref, 1.5e-2, "epipolar attention (mask)")
     assert torch.equal(out, out_m), "F-evaluated and mask-driven attention must take identical decisions"
+    # tile map: skipping whole key tiles must not change a single bit, and the map must cover every unmasked pair
+    tmap = ops.epipolar_tile_map(Fm.to(DEV).contiguous(), T, H, W, d)
+    if tmap is not None:
+        out_t = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm.to(DEV).contiguous(), epi_grid=(T, H, W),
+                              epi_d=d, epi_tile_map=tmap)
+        assert torch.equal(out, out_t)
+        nt = (L + 127) // 128
+        bits = torch.tensor([[(int(tmap[0, qt, j >> 5]) >> (j & 31)) & 1 for j in range(nt)] for qt in range(nt)], dtype=torch.bool)
+        mpad = torch.zeros(nt * 128, nt * 128, dtype=torch.bool)
+        mpad[:L, :L] = mask[0].cpu()
+        occ = mpad.view(nt, 128, nt, 128).any(dim=3).any(dim=1)
+        assert bool((bits | ~occ).all()), "tile map cleared a tile that contains an attended pair"
+        print(f"tile map {kind} {H}x{W}: {bits.float().mean():.3f} of tiles visited, {occ.float().mean():.3f} truly occupied")
 
 
 @pytest.mark.parametrize("B,T,HW,heads", [(1, 16, 1024, 5), (2, 16, 64, 20), (1, 16, 256, 8), (1, 8, 16, 4)])
