@@ -137,8 +137,9 @@ def to_device_conditioning(host, cam_host, device, static=None):
         # a new video: its poses arrive from the host and F is rebuilt (tiny 4x4 algebra) into the static buffer
         rel = camera.relative_c2w(cam_host["w2c"], torch.zeros(cam_host["w2c"].shape[0], dtype=torch.long))
         static["cam"]["epipolar_F"].copy_(camera.fundamental_matrices(cam_host["K"], rel), non_blocking=True)
-        from camc2v_b200.modules import refresh_camera_caches
+        from camc2v_b200.modules import refresh_camera_caches, refresh_context_caches
         refresh_camera_caches()           # tile maps / channels-last Pluecker copies follow the refilled static buffers
+        refresh_context_caches(static.get("_model"))   # bf16 context tokens + every layer's projected context K/V
     static["_uploaded"] = True
     nbytes += cam_host["K"].numel() * 4 + cam_host["w2c"].numel() * 4
     cond = {"c_crossattn": [static["ctx_cond"]], "c_concat": [static["c_concat"]], "camera_condition": static["cam"]}
@@ -327,6 +328,7 @@ def main():
     host["pluker"] = [pin(p) for p in host["pluker"]]
     sampler.concurrent_passes = not args.serial_passes
     cond, uc, static, cond_bytes = to_device_conditioning(host, cam_host, device)
+    static["_model"] = model
     kw = dict(unconditional_guidance_scale=3.5, unconditional_conditioning=uc, guidance_rescale=0.7, fs=static["fs"],
               enable_camera_condition=True, use_cuda_graph=not args.no_graph)
     steps_per_video = 25

@@ -60,8 +60,13 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     if (d->ldo % 4 != 0 || (d->residual && d->ldr % 4 != 0)) return ERR_UNSUPPORTED;
     if (d->taps != 1 && d->taps != 3 && d->taps != 9) return ERR_BAD_ARG;
     if (d->rowbias && d->rows_per_group <= 0) return ERR_BAD_ARG;
-    const int bn = c2v_gemm_tile_n(d->N, d->epi);
+    int bn = c2v_gemm_tile_n(d->N, d->epi);
     if (bn == 0) return ERR_UNSUPPORTED;
+    if (d->epi == C2V_EPI_LINEAR && d->splitk <= 1 && d->N % 64 == 0 && bn > 64) {
+        // few output tiles and no split-K (shallow K): narrower N tiles put more CTAs (more TMA streams) on the machine
+        const int mt = (d->M + 127) / 128;
+        if (mt * ((d->N + bn - 1) / bn) < 120) bn = 64;
+    }
     if (d->epi == C2V_EPI_GEGLU && (!d->out_bf16 || d->rowbias || d->residual)) return ERR_BAD_ARG;
 
     GemmKernelArgs a;

@@ -167,6 +167,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             const bool leader = threadIdx.x == 64;      // warp 2, lane 0: owns the bulk async-group of the stores
             mbar_wait<200>(acc_bar, 0);                 // every MMA has completed: accumulator valid, smem stages free
             tc_fence_after();
+            if (p.epi == EPI_GEGLU) {
+                // x * gelu(gate): value columns [0, BN/2) and gate columns [BN/2, BN) of this tile; bf16 result staged per
+                // 16-column chunk (32-byte rows) and written by TMA stores
+                constexpr int HALF = BN / 2;
+                const int no = blockIdx.y * HALF;
+#pragma unroll 1
+                for (int c = 0; c < HALF; c += 16) {
+                    uint32_t xv[16], gv[16];
+                    tmem_ld16(trow + c, xv);
+                    tmem_ld16(trow + HALF + c, gv);
+                    tmem_ld_wait();
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
+                        float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
+                        if (p.bias) {
+                            x0 += p.bias[n0 + c + j];
+                            x1 += p.bias[n0 + c + j + 1];
+                            g0 += p.bias[n0 + HALF + c + j];
+                            g1 += p.bias[n0 + HALF + c + j + 1];
+                        }
+                        pk[j / 2] = pack_bf16(x0 * gelu_erf_fast(g0), x1 * gelu_erf_fast(g1));
+                    }
+                    uint8_t* buf = smem + (c >> 4) * 4096;
+                    uint4* dst = reinterpret_cast<uint4*>(buf + r * 32);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    fence_proxy_async();
+                    named_bar_sync(1, 128);
+                    if (leader) {
+                        tma_store_3d(&p.tmO, buf, no + c, m0, 0);
+                        tma_store_commit();
+                    }
+                }
+                if (leader) tma_store_wait_read_all();
+                tc_fence_before();
+            } else {
             if (leader && has_res) {
                 for (int c = 0; c < NCH; ++c) {
                     if (n0 + c * 32 >= p.N) break;
@@ -235,6 +273,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             }
             if (leader) tma_store_wait_read_all();
             tc_fence_before();
+            }
         } else {
         mbar_wait<200>(acc_bar, 0);
         tc_fence_after();
@@ -264,7 +303,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                             g0 += p.bias[n0 + HALF + c + j];
                             g1 += p.bias[n0 + HALF + c + j + 1];
                         }
-                        pk[j / 2] = pack_bf16(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+                        pk[j / 2] = pack_bf16(x0 * gelu_erf_fast(g0), x1 * gelu_erf_fast(g1));
                     }
                     uint4* dst = reinterpret_cast<uint4*>(o + c);
                     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);

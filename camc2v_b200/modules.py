@@ -67,6 +67,7 @@ class ContextPack:
     image: Optional[torch.Tensor]   # [Bi*Li, 1024]
     image_div: int
     image_len: int
+    gen: int = 0                    # bumped whenever the token matrices are re-filled in place (invalidates projected K/V)
 
 
 @dataclass
@@ -386,14 +387,32 @@ class CrossAttention(_Prepared):
         o = ops.attention_temporal(qkv, dm.B, dm.T, dm.HW, self.heads)
         return ops.linear(o, p["wo"], bias=p["bo"], residual=residual, out_dtype=out_dtype)
 
+    def _context_kv(self, ctx: "ContextPack", w: torch.Tensor, slot: str):
+        """K|V projection of the text / image context tokens.  The context is a per-sample constant (it does not depend on
+        the timestep), so the projection is computed once per sample and layer — the reference recomputes it for each of
+        the 16 frames, 2 passes and 25 steps.  Cached per token buffer; when the buffer is refilled in place (`ctx.gen`
+        changes) the projection is recomputed into the same output buffer, which keeps CUDA-graph pointers valid."""
+        src = ctx.text if slot == "text" else ctx.image
+        cache = self.__dict__.setdefault("_ctx_cache", {})
+        key = (slot, src.data_ptr(), tuple(src.shape))
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) > 8:
+                cache.clear()
+            ent = cache[key] = [ctx.gen, ops.linear(src, w, out_dtype=BF16), ctx, w, slot]
+        elif ent[0] != ctx.gen:
+            ent[0] = ctx.gen
+            ops.linear(src, w, out=ent[1])
+        return ent[1]
+
     def cross(self, n: torch.Tensor, ctx: ContextPack, bq: int, lq: int, residual, out_dtype=F32):
         p = self.pk()
         C = self.heads * 64
         q = ops.linear(n, p["wq"], out_dtype=BF16)
-        kv = ops.linear(ctx.text, p["wkv"], out_dtype=BF16)                 # once per sample, not per frame
+        kv = self._context_kv(ctx, p["wkv"], "text")                   # once per sample, not per frame / pass / step
         o = ops.attention(q, kv[:, :C], kv[:, C:], bq, lq, ctx.text_len, self.heads, kv_div=ctx.text_div)
         if self.image_cross_attention and ctx.image is not None:
-            kvi = ops.linear(ctx.image, p["wkv_ip"], out_dtype=BF16)
+            kvi = self._context_kv(ctx, p["wkv_ip"], "image")
             ops.attention(q, kvi[:, :C], kvi[:, C:], bq, lq, ctx.image_len, self.heads, kv_div=ctx.image_div, out=o,
                           out_scale=p["gate"], accumulate=True)
         return ops.linear(o, p["wo"], bias=p["bo"], residual=residual, out_dtype=out_dtype)
@@ -421,24 +440,66 @@ def _transpose_tokens(x: torch.Tensor, a: int, b: int, dtype=None):
     return y if dtype is None else y.to(dtype)
 
 
+_CONTEXT_CACHE: Dict[tuple, list] = {}
+
+
 def make_context_pack(context: torch.Tensor, T: int, text_len: int = 77, per_frame: Optional[bool] = None) -> ContextPack:
     """context [B, L, D] as given to UNetModel.forward.  Frame broadcast rule of modified_forwards.py:37-44:
-    L == 77 + 16*T -> frame f sees its own 16 image tokens, otherwise every frame sees all image tokens."""
+    L == 77 + 16*T -> frame f sees its own 16 image tokens, otherwise every frame sees all image tokens.
+    The pack (bf16 text / image token matrices) is cached per context buffer: the context is constant over the sampling
+    loop, and stable buffers let every cross-attention layer keep its projected K/V."""
+    key = (context.data_ptr(), tuple(context.shape), T, text_len, per_frame, str(context.device))
+    ent = _CONTEXT_CACHE.get(key)
+    if ent is not None and ent[0] == context._version:
+        return ent[1]
+    pack = _make_context_pack(context, T, text_len, per_frame, ent[1] if ent is not None else None)
+    if len(_CONTEXT_CACHE) > 16:
+        _CONTEXT_CACHE.clear()
+    _CONTEXT_CACHE[key] = [context._version, pack, context]
+    return pack
+
+
+def refresh_context_caches(model: Optional[nn.Module] = None) -> None:
+    """After refilling static context buffers in place (new video, CUDA-graph replay): recast the token matrices and
+    re-project every layer's cached context K/V into their existing buffers."""
+    for key, ent in list(_CONTEXT_CACHE.items()):
+        ctx = ent[2]
+        if ent[0] != ctx._version:
+            ent[1] = _make_context_pack(ctx, key[2], key[3], key[4], ent[1])
+            ent[0] = ctx._version
+    if model is not None:
+        for m in model.modules():
+            cache = m.__dict__.get("_ctx_cache")
+            if cache:
+                for e in cache.values():
+                    if e[0] != e[2].gen:
+                        m._context_kv(e[2], e[3], e[4])
+
+
+def _cast_into(src_f32: torch.Tensor, old: Optional[torch.Tensor]):
+    if old is None:
+        return ops.cast_bf16(src_f32)
+    from . import _lib
+    _lib.call("c2v_cast_bf16", src_f32.data_ptr(), old.data_ptr(), src_f32.numel(), torch.cuda.current_stream().cuda_stream)
+    return old
+
+
+def _make_context_pack(context: torch.Tensor, T: int, text_len: int, per_frame: Optional[bool], old: Optional[ContextPack]) -> ContextPack:
     B, L, D = context.shape
     if per_frame is None:
         per_frame = (L == text_len + T * 16)
     ctx = _f32(context)
-    text = ops.cast_bf16(ctx[:, :text_len].contiguous().view(B * text_len, D))
+    text = _cast_into(ctx[:, :text_len].contiguous().view(B * text_len, D), old.text if old is not None else None)
     image, idiv, ilen = None, T, 0
     if L > text_len:
         img = ctx[:, text_len:].contiguous()
         if per_frame:
             ilen, idiv = 16, 1
-            image = ops.cast_bf16(img.view(B * T * 16, D))
+            image = _cast_into(img.view(B * T * 16, D), old.image if old is not None else None)
         else:
             ilen, idiv = L - text_len, T
-            image = ops.cast_bf16(img.view(B * ilen, D))
-    return ContextPack(text, T, text_len, image, idiv, ilen)
+            image = _cast_into(img.view(B * ilen, D), old.image if old is not None else None)
+    return ContextPack(text, T, text_len, image, idiv, ilen, (old.gen + 1) if old is not None else 0)
 
 
 class EpipolarCrossAttention(_Prepared):
