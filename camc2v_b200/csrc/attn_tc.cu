@@ -291,8 +291,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                     const int key0 = tile_key0 + c * 32;
                     if (plain && key0 + 32 <= klim) {             // dense attention, full chunk: no predicate at all
                         bm = 0xffffffffu;
+                        float mx1 = -INFINITY;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        for (int i = 0; i < 32; i += 4) {
+                            mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+                        }
+                        mx = fmaxf(mx, mx1);
                     } else {
                         uint32_t mw[8];
                         if (mrow && main_seg) {
@@ -354,12 +359,26 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                     tmem_ld32(t_s + c * 32, v);
                     tmem_ld_wait();
                     const uint32_t bm = bits[c];
+                    if (__all_sync(0xffffffffu, bm == 0xffffffffu)) {
+                        // dense chunk (no mask, no ragged tail): no per-element predicate, two independent row-sum chains
+                        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float e0 = (bm >> i) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use)) : 0.f;
-                        const float e1 = (bm >> (i + 1)) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use)) : 0.f;
-                        lsum += e0 + e1;
-                        pk[c * 16 + i / 2] = pack_bf16(e0, e1);
+                        for (int i = 0; i < 32; i += 2) {
+                            const float e0 = fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use));
+                            const float e1 = fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use));
+                            l0 += e0;
+                            l1 += e1;
+                            pk[c * 16 + i / 2] = pack_bf16(e0, e1);
+                        }
+                        lsum += l0 + l1;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float e0 = (bm >> i) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use)) : 0.f;
+                            const float e1 = (bm >> (i + 1)) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use)) : 0.f;
+                            lsum += e0 + e1;
+                            pk[c * 16 + i / 2] = pack_bf16(e0, e1);
+                        }
                     }
                 } else {
 #pragma unroll
