@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "csrc", "_obj")
 SOURCES = ["api.cu", "gemm_tc.cu", "attn_tc.cu", "attn_t16.cu", "norm.cu", "elementwise.cu", "epipolar.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr"]
+         "--expt-relaxed-constexpr"] + os.environ.get("C2V_NVCC_EXTRA", "").split()
 
 
 def _stale(target: str, deps) -> bool:

@@ -284,12 +284,23 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                 const bool plain = !(epi && main_seg) && !(mrow && main_seg);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    const int key0 = tile_key0 + c * 32;
+                    if (plain && key0 >= klim) {                  // chunk past the last key (ragged tail, register tokens)
+                        bits[c] = 0;
+                        continue;
+                    }
+                    anyc |= 1u << c;
                     uint32_t v[32];
                     tmem_ld32(t_s + c * 32, v);
                     tmem_ld_wait();
                     uint32_t bm = 0;
-                    const int key0 = tile_key0 + c * 32;
-                    if (plain && key0 + 32 <= klim) {             // dense attention, full chunk: no predicate at all
+                    if (plain && key0 + 32 > klim) {              // ragged last chunk: keys [0, nv) valid, everything in registers
+                        const int nv = klim - key0;               // 1..31, warp-uniform
+                        bm = (1u << nv) - 1u;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    } else if (plain) {                           // dense attention, full chunk: no predicate at all
                         bm = 0xffffffffu;
                         float mx1 = -INFINITY;
 #pragma unroll
@@ -343,7 +354,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                     }
                     bits[c] = bm;
                 }
-                anyc = 0xfu;
             }
             const float m_new = fmaxf(m_run, mx * p.scale_log2);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;

@@ -145,6 +145,10 @@ def single(which):
     elif which == "attn0":
         q, kv = rb(16 * 1024, 320), rb(16 * 1024, 640)
         fn = lambda: ops.attention(q, kv[:, :320], kv[:, 320:], 16, 1024, 1024, 5)
+    elif which in ("attn77", "attn16"):
+        lk, div = (77, 16) if which == "attn77" else (16, 1)
+        q, kv = rb(16 * 1024, 320), rb((16 // div) * lk, 640)
+        fn = lambda: ops.attention(q, kv[:, :320], kv[:, 320:], 16, 1024, lk, 5, kv_div=div)
     else:
         raise SystemExit(which)
     print(which, f"{timeit(fn):.1f} us")
