@@ -62,6 +62,21 @@ __device__ __forceinline__ EpiLine epi_line(const float* __restrict__ f, float x
 
 // LOGW >= 3 selects the fast epipolar predicate for square 2^LOGW x 2^LOGW key grids with pixel pitch D
 // (LOGW = 0: dense attention, materialised masks and arbitrary grids).
+constexpr uint32_t NEG_INF_BITS = 0xff800000u;
+
+// max of 32 scores held as raw bits: four independent chains of 3-input maxima (FMNMX3)
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+    float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        a0 = fmaxf(a0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        a1 = fmaxf(a1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+        a2 = fmaxf(a2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+        a3 = fmaxf(a3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+    }
+    return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+}
+
 template <int LOGW, int D>
 __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnKernelArgs p) {
     constexpr bool FAST = LOGW >= 3;
@@ -227,13 +242,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             const int jt = tile_list[j];              // key tile index (j counts visited tiles: barrier parities)
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            uint32_t bits[4];
             uint32_t anyc = 0;       // chunks in which at least one lane of this warp has a valid key (warp-uniform)
+            bool wrote = false;      // some chunk of S was rewritten with masked scores (warp-uniform)
             float mx = -INFINITY;
             const bool main_seg = jt < n_main;
             const int klim = main_seg ? p.lk : p.lk2;
             const int tile_key0 = main_seg ? jt * AT_BN : 0;
-            // ---- pass 1: validity mask + row max ----
+            // ---- pass 1: row max; masked / out-of-range scores are replaced by -inf IN TMEM (tcgen05.st), so that pass 2 is
+            //      the same predicate-free exp2 loop for every flavour of attention (exp2(-inf) = 0) ----
             if (FAST && epi && main_seg) {
                 // Square power-of-two key grid: a 32-key chunk is RPC whole image rows of one frame, pixel x of column i
                 // is a compile-time constant and the reference's mask predicate costs FMUL+FFMA+FADD+FSETP per element.
@@ -262,7 +278,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                         const float w1 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, (float)(W - 1) * DF + OFFC)), line.l2);
                         maybe |= !((w0 > thr_m && w1 > thr_m) || (w0 < -thr_m && w1 < -thr_m));
                     }
-                    uint32_t bm = 0;
                     if (__any_sync(0xffffffffu, maybe)) {
                         uint32_t v[32];
                         tmem_ld32(t_s + c * 32, v);
@@ -271,44 +286,35 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                         for (int i = 0; i < 32; ++i) {
                             const float xj = (float)(i & (W - 1)) * DF + OFFC;      // compile-time constant
                             const float wv = __fadd_rn(__fmaf_rn(line.l1, yr[i >> LOGW], __fmul_rn(line.l0, xj)), line.l2);
-                            if (fabsf(wv) < p.epi_thr) {
-                                bm |= 1u << i;
-                                mx = fmaxf(mx, __uint_as_float(v[i]));
-                            }
+                            v[i] = fabsf(wv) < p.epi_thr ? v[i] : NEG_INF_BITS;
+                        }
+                        const float cm = max32(v);
+                        if (__any_sync(0xffffffffu, cm > -INFINITY)) {
+                            anyc |= 1u << c;
+                            wrote = true;
+                            tmem_st32(t_s + c * 32, v);
+                            mx = fmaxf(mx, cm);
                         }
                     }
-                    bits[c] = bm;
-                    anyc |= (__any_sync(0xffffffffu, bm != 0) ? 1u : 0u) << c;
                 }
             } else {
                 const bool plain = !(epi && main_seg) && !(mrow && main_seg);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int key0 = tile_key0 + c * 32;
-                    if (plain && key0 >= klim) {                  // chunk past the last key (ragged tail, register tokens)
-                        bits[c] = 0;
-                        continue;
-                    }
+                    if (plain && key0 >= klim) continue;          // chunk past the last key (ragged tail, register tokens)
                     anyc |= 1u << c;
                     uint32_t v[32];
                     tmem_ld32(t_s + c * 32, v);
                     tmem_ld_wait();
-                    uint32_t bm = 0;
-                    if (plain && key0 + 32 > klim) {              // ragged last chunk: keys [0, nv) valid, everything in registers
+                    if (plain && key0 + 32 <= klim) {             // dense attention, full chunk: no predicate, S stays as it is
+                        mx = fmaxf(mx, max32(v));
+                        continue;
+                    }
+                    if (plain) {                                  // ragged last chunk: keys [0, nv) valid, everything in registers
                         const int nv = klim - key0;               // 1..31, warp-uniform
-                        bm = (1u << nv) - 1u;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    } else if (plain) {                           // dense attention, full chunk: no predicate at all
-                        bm = 0xffffffffu;
-                        float mx1 = -INFINITY;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-                            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
-                        }
-                        mx = fmaxf(mx, mx1);
+                        for (int i = 0; i < 32; ++i) v[i] = i < nv ? v[i] : NEG_INF_BITS;
                     } else {
                         uint32_t mw[8];
                         if (mrow && main_seg) {
@@ -329,72 +335,67 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                                 }
                             }
                         }
+                        if (epi && main_seg) {                    // generic grid (non power-of-two / 4x4): slow but exact
 #pragma unroll 4
-                        for (int i = 0; i < 32; ++i) {
-                            const int key = key0 + i;
-                            bool ok = key < klim;
-                            if (mrow && main_seg) ok = ok && ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) != 0;
-                            if (epi && main_seg && ok) {          // generic grid (non power-of-two / 4x4): slow but exact
-                                const int t2 = key / HW;
-                                if (t2 != cur_t2) {
-                                    cur_t2 = t2;
-                                    line = epi_line(Frow + t2 * 9, xi, yi);
+                            for (int i = 0; i < 32; ++i) {
+                                const int key = key0 + i;
+                                bool ok = key < klim;
+                                if (mrow) ok = ok && ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) != 0;
+                                if (ok) {
+                                    const int t2 = key / HW;
+                                    if (t2 != cur_t2) {
+                                        cur_t2 = t2;
+                                        line = epi_line(Frow + t2 * 9, xi, yi);
+                                    }
+                                    const int pj = key - t2 * HW;
+                                    const float xj = __fadd_rn(__fmul_rn((float)(pj % p.epi_W), (float)p.epi_d), p.epi_off);
+                                    const float yj = __fadd_rn(__fmul_rn((float)(pj / p.epi_W), (float)p.epi_d), p.epi_off);
+                                    const float dist = fabsf(__fadd_rn(__fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj)), line.l2));
+                                    ok = dist < p.epi_thr;
                                 }
-                                const int pj = key - t2 * HW;
-                                const float xj = __fadd_rn(__fmul_rn((float)(pj % p.epi_W), (float)p.epi_d), p.epi_off);
-                                const float yj = __fadd_rn(__fmul_rn((float)(pj / p.epi_W), (float)p.epi_d), p.epi_off);
-                                const float dist = fabsf(__fadd_rn(__fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj)), line.l2));
-                                ok = dist < p.epi_thr;
+                                if (!ok) v[i] = NEG_INF_BITS;
                             }
-                            if (ok) {
-                                bm |= 1u << i;
-                                mx = fmaxf(mx, __uint_as_float(v[i]));
+                        } else {                                  // materialised mask bytes (+ ragged tail)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const bool ok = (key0 + i < klim) && ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) != 0;
+                                v[i] = ok ? v[i] : NEG_INF_BITS;
                             }
                         }
                     }
-                    bits[c] = bm;
+                    wrote = true;
+                    tmem_st32(t_s + c * 32, v);
+                    mx = fmaxf(mx, max32(v));
                 }
             }
+            if (wrote) tmem_st_wait();
             const float m_new = fmaxf(m_run, mx * p.scale_log2);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
             const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
             l_run *= alpha;
             // ---- pass 2: probabilities ----
             uint32_t pk[64];
-            float lsum = 0.f;
+            float l0 = 0.f, l1 = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if ((anyc >> c) & 1u) {
                     uint32_t v[32];
                     tmem_ld32(t_s + c * 32, v);
                     tmem_ld_wait();
-                    const uint32_t bm = bits[c];
-                    if (__all_sync(0xffffffffu, bm == 0xffffffffu)) {
-                        // dense chunk (no mask, no ragged tail): no per-element predicate, two independent row-sum chains
-                        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float e0 = fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use));
-                            const float e1 = fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use));
-                            l0 += e0;
-                            l1 += e1;
-                            pk[c * 16 + i / 2] = pack_bf16(e0, e1);
-                        }
-                        lsum += l0 + l1;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float e0 = (bm >> i) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use)) : 0.f;
-                            const float e1 = (bm >> (i + 1)) & 1u ? fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use)) : 0.f;
-                            lsum += e0 + e1;
-                            pk[c * 16 + i / 2] = pack_bf16(e0, e1);
-                        }
+                    for (int i = 0; i < 32; i += 2) {
+                        const float e0 = fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use));
+                        const float e1 = fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use));
+                        l0 += e0;
+                        l1 += e1;
+                        pk[c * 16 + i / 2] = pack_bf16(e0, e1);
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) pk[c * 16 + i] = 0u;
                 }
             }
+            const float lsum = l0 + l1;
             l_run += lsum;
             m_run = m_new;
             tc_fence_before();
