@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcamc2v_b200.so")
+LIB_PATH = os.environ.get("CAMC2V_B200_LIB") or os.path.join(_HERE, "libcamc2v_b200.so")   # env override: A/B builds in tools/
 
 A_PLAIN, A_CONV2D, A_CONVT = 0, 1, 2
 EPI_LINEAR, EPI_GEGLU = 0, 1

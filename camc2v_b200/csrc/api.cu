@@ -224,11 +224,12 @@ int c2v_attention(const c2v_attn_desc* d, void* stream) {
     memset(&a, 0, sizeof(a));
     const int hd = d->heads * 64;
     const int bk = (d->bq + d->kv_div - 1) / d->kv_div;
-    const uint32_t box[3] = {64, 128, 1};
+    const uint32_t qbox[3] = {64, 128, 1};    // 128 queries per CTA
+    const uint32_t box[3] = {64, 64, 1};      // 64 keys per tile
     {
         const uint64_t dims[3] = {(uint64_t)hd, (uint64_t)d->lq, (uint64_t)d->bq};
         const uint64_t strides[2] = {(uint64_t)d->ldq * 2, (uint64_t)d->q_bstride * 2};
-        if (!make_tmap_bf16(&a.tmQ, d->q, 3, dims, strides, box)) return ERR_TMA_ENCODE;
+        if (!make_tmap_bf16(&a.tmQ, d->q, 3, dims, strides, qbox)) return ERR_TMA_ENCODE;
     }
     {
         const uint64_t dims[3] = {(uint64_t)hd, (uint64_t)d->lk, (uint64_t)bk};
@@ -247,7 +248,7 @@ int c2v_attention(const c2v_attn_desc* d, void* stream) {
     a.out_scale = d->out_scale;
     a.accumulate = d->accumulate;
     if (d->k2 || d->v2 || d->lk2 > 0) {
-        if (!d->k2 || !d->v2 || d->lk2 <= 0 || d->lk2 > 128 || (d->ldk2 | d->ldv2) % 8 != 0) return ERR_BAD_ARG;
+        if (!d->k2 || !d->v2 || d->lk2 <= 0 || d->lk2 > 64 || (d->ldk2 | d->ldv2) % 8 != 0) return ERR_BAD_ARG;
         const uint64_t dims[3] = {(uint64_t)hd, (uint64_t)d->lk2, 1};
         const uint64_t sk[2] = {(uint64_t)d->ldk2 * 2, (uint64_t)d->ldk2 * 2 * d->lk2};
         const uint64_t sv[2] = {(uint64_t)d->ldv2 * 2, (uint64_t)d->ldv2 * 2 * d->lk2};
@@ -286,7 +287,7 @@ int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, 
     return epipolar_mask_launch(F, out, B, T, H, W, d, (cudaStream_t)stream);
 }
 
-int c2v_epipolar_tile_map_words(int T, int H, int W) { return ((T * H * W + 127) / 128 + 31) / 32; }
+int c2v_epipolar_tile_map_words(int T, int H, int W) { return ((T * H * W + 63) / 64 + 31) / 32; }   // 64-key tiles
 
 int c2v_epipolar_tile_map(const float* F, uint32_t* map, int B, int T, int H, int W, int d, void* stream) {
     if (!F || !map || B <= 0 || B > 65535) return ERR_BAD_ARG;

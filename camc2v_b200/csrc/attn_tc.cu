@@ -3,12 +3,15 @@
 //   softmax path (attention.py:105-129) and F.scaled_dot_product_attention with the boolean epipolar mask
 //   (R/model/modules/epipolar.py:99).
 //
-// One CTA = 128 query rows of one (batch, head).  Per 128-key tile:
-//     S = Q K^T          tcgen05.mma 128x128x16 (x4), both operands K-major in 128B-swizzled smem (TMA)
-//     P = softmax tile   4 warps, one query row per thread, S read from TMEM in two passes (max, then exp)
-//     O += P V           tcgen05.mma 128x64x16 (x8), P from smem (written swizzled by the softmax warps),
+// One CTA = 128 query rows of one (batch, head).  Per 64-key tile:
+//     S = Q K^T          tcgen05.mma 128x64x16 (x4), both operands K-major in 128B-swizzled smem (TMA); S is double-buffered
+//                        in TMEM so that S(j+1) is computed while the softmax warps are still reading S(j)
+//     P = softmax tile   4 warps, one query row per thread, S read from TMEM in two passes (max + mask write-back, then exp)
+//     O += P V           tcgen05.mma 128x64x16 (x4), P from smem (written swizzled by the softmax warps),
 //                        V as MN-major operand straight from its natural [key, d] layout
 // The running output O stays in TMEM; it is rescaled in place (tcgen05.ld/st) only when a row maximum grows.
+// 64-key tiles (two image rows of a 32x32 latent frame) keep the epipolar tile map fine-grained: only tiles that can
+// contain an attended pair are ever loaded, multiplied or soft-maxed.
 //
 // Epipolar mode: the reference materialises a bool mask [B, L, L] (268 MB per sample at 32x32x16) and
 // reads it in every layer.  Here the mask is evaluated inside the softmax pass from the 3x3 fundamental
@@ -21,27 +24,38 @@
 namespace c2v {
 
 constexpr int AT_BM = 128;   // query rows per CTA
-constexpr int AT_BN = 128;   // keys per tile
+constexpr int AT_BN = 64;    // keys per tile
 constexpr int AT_D = 64;
-constexpr int AT_KV_STAGES = 2;
+#ifndef C2V_AT_S_BUFS
+#define C2V_AT_S_BUFS 2
+#endif
+#ifndef C2V_AT_KV_STAGES
+#define C2V_AT_KV_STAGES 4
+#endif
+#ifndef C2V_AT_MIN_CTAS
+#define C2V_AT_MIN_CTAS 2
+#endif
+constexpr int AT_S_BUFS = C2V_AT_S_BUFS;        // S accumulators in TMEM
+constexpr int AT_KV_STAGES = C2V_AT_KV_STAGES;
+constexpr int AT_MIN_CTAS = C2V_AT_MIN_CTAS;    // resident CTAs per SM the register budget is sized for
 constexpr int AT_THREADS = 192;
 
 constexpr int AT_Q_BYTES = AT_BM * AT_D * 2;        // 16 KB
-constexpr int AT_K_BYTES = AT_BN * AT_D * 2;        // 16 KB
-constexpr int AT_V_BYTES = AT_BN * AT_D * 2;        // 16 KB
-constexpr int AT_P_BYTES = AT_BM * AT_BN * 2;       // 32 KB (two 64-key halves)
+constexpr int AT_K_BYTES = AT_BN * AT_D * 2;        // 8 KB
+constexpr int AT_V_BYTES = AT_BN * AT_D * 2;        // 8 KB
+constexpr int AT_P_BYTES = AT_BM * AT_BN * 2;       // 16 KB (128 rows x one 128-byte swizzle atom)
 constexpr int AT_OFF_Q = 0;
 constexpr int AT_OFF_K = AT_OFF_Q + AT_Q_BYTES;
 constexpr int AT_OFF_V = AT_OFF_K + AT_KV_STAGES * AT_K_BYTES;
 constexpr int AT_OFF_P = AT_OFF_V + AT_KV_STAGES * AT_V_BYTES;
 constexpr int AT_OFF_BAR = AT_OFF_P + AT_P_BYTES;
-constexpr int AT_OFF_LIST = AT_OFF_BAR + 128;                   // active key-tile list (uint16), <= AT_MAX_TILES entries
-constexpr int AT_MAX_TILES = 384;
+constexpr int AT_OFF_LIST = AT_OFF_BAR + 256;                   // active key-tile list (uint16), <= AT_MAX_TILES entries
+constexpr int AT_MAX_TILES = 1024;                              // 65 472 keys + the register-token segment
 constexpr int AT_SMEM = AT_OFF_LIST + AT_MAX_TILES * 2;
 
-constexpr uint32_t AT_TMEM_COLS = 256;
-constexpr uint32_t AT_TM_S = 0;       // S accumulator: columns [0,128)
-constexpr uint32_t AT_TM_O = 128;     // O accumulator: columns [128,192)
+constexpr uint32_t AT_TM_S = 0;                       // S accumulator(s): AT_S_BUFS x 64 columns
+constexpr uint32_t AT_TM_O = AT_S_BUFS * AT_BN;       // O accumulator: 64 columns
+constexpr uint32_t AT_TMEM_COLS = AT_TM_O + AT_D <= 128 ? 128 : 256;
 
 struct EpiLine {
     float l0, l1, l2;
@@ -78,18 +92,22 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
 }
 
 template <int LOGW, int D>
-__global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnKernelArgs p) {
+#if C2V_AT_MIN_CTAS == 3
+__global__ void __maxnreg__(112) attn_tc_kernel(const __grid_constant__ AttnKernelArgs p) {
+#else
+__global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const __grid_constant__ AttnKernelArgs p) {
+#endif
     constexpr bool FAST = LOGW >= 3;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
     uint64_t* q_full = bars + 0;
-    uint64_t* kv_full = bars + 1;    // [2]
-    uint64_t* kv_empty = bars + 3;   // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* s_free = bars + 6;
-    uint64_t* p_full = bars + 7;
-    uint64_t* pv_done = bars + 8;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* kv_full = bars + 1;    // [AT_KV_STAGES]
+    uint64_t* kv_empty = bars + 5;   // [AT_KV_STAGES]  (AT_KV_STAGES <= 4)
+    uint64_t* s_full = bars + 9;     // [2]  S(j) is in TMEM buffer j & 1
+    uint64_t* s_free = bars + 11;    // [2]
+    uint64_t* p_full = bars + 13;
+    uint64_t* pv_done = bars + 14;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * AT_BM;
@@ -116,8 +134,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
         }
-        mbar_init(s_full, 1);
-        mbar_init(s_free, 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 128);
+        }
         mbar_init(p_full, 128);
         mbar_init(pv_done, 1);
         fence_barrier_init();
@@ -130,7 +150,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
     // sample by epi_tile_map_kernel with the same conservative test as the in-tile row skip) tiles that cannot contain an
     // unmasked pair are never loaded, multiplied or soft-maxed.
     uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + AT_OFF_LIST);
-    int* n_act_s = reinterpret_cast<int*>(bars + 10);
+    int* n_act_s = reinterpret_cast<int*>(bars + 16);
     if (warp == 2) {
         const uint32_t* map = p.tile_map ? p.tile_map + ((size_t)b * gridDim.x + blockIdx.x) * p.tile_map_words : nullptr;
         int cnt = 0;
@@ -176,17 +196,18 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, AT_D, 0, 1);   // B = V is MN-major
         const uint32_t q_addr = smem_u32(smem + AT_OFF_Q);
         const uint32_t p_addr = smem_u32(smem + AT_OFF_P);
-        auto issue_qk = [&](int j) {                  // j = iteration index over the active-tile list
+        auto issue_qk = [&](int j) {                  // j = iteration index over the active-tile list; S(j) -> TMEM buffer j & 1
             const int s = j % AT_KV_STAGES;
             mbar_wait<40>(&kv_full[s], (j / AT_KV_STAGES) & 1);
-            if (j > 0) mbar_wait<40>(s_free, (j - 1) & 1);
+            if (j >= AT_S_BUFS) mbar_wait<40>(&s_free[j % AT_S_BUFS], ((j - AT_S_BUFS) / AT_S_BUFS) & 1);   // softmax(j - bufs) done
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t qd = umma_desc_sw128(q_addr);
                 const uint64_t kd = umma_desc_sw128(smem_u32(smem + AT_OFF_K + s * AT_K_BYTES));
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tmem_base + AT_TM_S, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
-                umma_commit(s_full);
+                for (int k = 0; k < AT_D / 16; ++k)
+                    umma_bf16_ss(tmem_base + AT_TM_S + (uint32_t)(j % AT_S_BUFS) * AT_BN, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+                umma_commit(&s_full[j % AT_S_BUFS]);
             }
             __syncwarp();
         };
@@ -194,14 +215,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         issue_qk(0);
         for (int j = 0; j < n_act; ++j) {
             const int s = j % AT_KV_STAGES;
-            if (j + 1 < n_act) issue_qk(j + 1);       // overlaps with the softmax warps writing P(j)
+            if (j + 1 < n_act) issue_qk(j + 1);       // S(j+1) is computed while the softmax warps work on S(j)
             mbar_wait<40>(p_full, j & 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t v_addr = smem_u32(smem + AT_OFF_V + s * AT_V_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < AT_BN / 16; ++ks) {
-                    const uint64_t pd = umma_desc_sw128(p_addr + (ks / 4) * (AT_BM * 128)) + 2 * (ks % 4);
+                    const uint64_t pd = umma_desc_sw128(p_addr) + 2 * ks;
                     const uint64_t vd = umma_desc_sw128(v_addr + ks * 16 * 128);
                     umma_bf16_ss(tmem_base + AT_TM_O, pd, vd, idesc_pv, (j | ks) != 0);
                 }
@@ -215,7 +236,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         const int lg = warp & 3;
         const int r = lg * 32 + lane_id();
         const int qi = q0 + r;                                     // query index inside the batch
-        const uint32_t t_s = tmem_base + AT_TM_S + ((uint32_t)(lg * 32) << 16);
+        const uint32_t t_s0 = tmem_base + AT_TM_S + ((uint32_t)(lg * 32) << 16);
         const uint32_t t_o = tmem_base + AT_TM_O + ((uint32_t)(lg * 32) << 16);
         const bool epi = p.epi_F != nullptr;
         const unsigned char* mrow = p.mask ? p.mask + (size_t)b * p.mask_bstride + (size_t)min(qi, p.lq - 1) * p.lk : nullptr;
@@ -240,8 +261,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
 
         for (int j = 0; j < n_act; ++j) {
             const int jt = tile_list[j];              // key tile index (j counts visited tiles: barrier parities)
-            mbar_wait(s_full, j & 1);
+            mbar_wait(&s_full[j % AT_S_BUFS], (j / AT_S_BUFS) & 1);
             tc_fence_after();
+            const uint32_t t_s = t_s0 + (uint32_t)(j % AT_S_BUFS) * AT_BN;
             uint32_t anyc = 0;       // chunks in which at least one lane of this warp has a valid key (warp-uniform)
             bool wrote = false;      // some chunk of S was rewritten with masked scores (warp-uniform)
             float mx = -INFINITY;
@@ -257,7 +279,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                 constexpr int RPC = 32 / W;
                 constexpr float DF = (float)D, OFFC = (float)D * 0.5f - 0.5f;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < AT_BN / 32; ++c) {
                     const int key0 = tile_key0 + c * 32;
                     const int t2 = key0 >> (2 * LOGW);
                     if (t2 != cur_t2) {                     // warp-uniform: once per key frame
@@ -300,7 +322,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             } else {
                 const bool plain = !(epi && main_seg) && !(mrow && main_seg);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < AT_BN / 32; ++c) {
                     const int key0 = tile_key0 + c * 32;
                     if (plain && key0 >= klim) continue;          // chunk past the last key (ragged tail, register tokens)
                     anyc |= 1u << c;
@@ -336,7 +358,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                             }
                         }
                         if (epi && main_seg) {                    // generic grid (non power-of-two / 4x4): slow but exact
-#pragma unroll 4
+                            uint32_t okbits = 0;                  // rolled predicate loop; scores stay in registers
+#pragma unroll 1
                             for (int i = 0; i < 32; ++i) {
                                 const int key = key0 + i;
                                 bool ok = key < klim;
@@ -353,8 +376,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                                     const float dist = fabsf(__fadd_rn(__fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj)), line.l2));
                                     ok = dist < p.epi_thr;
                                 }
-                                if (!ok) v[i] = NEG_INF_BITS;
+                                okbits |= (ok ? 1u : 0u) << i;
                             }
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = (okbits >> i) & 1u ? v[i] : NEG_INF_BITS;
                         } else {                                  // materialised mask bytes (+ ragged tail)
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
@@ -373,34 +398,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
             const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
             l_run *= alpha;
-            // ---- pass 2: probabilities ----
-            uint32_t pk[64];
-            float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if ((anyc >> c) & 1u) {
-                    uint32_t v[32];
-                    tmem_ld32(t_s + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float e0 = fast_exp2(__fmaf_rn(__uint_as_float(v[i]), p.scale_log2, -m_use));
-                        const float e1 = fast_exp2(__fmaf_rn(__uint_as_float(v[i + 1]), p.scale_log2, -m_use));
-                        l0 += e0;
-                        l1 += e1;
-                        pk[c * 16 + i / 2] = pack_bf16(e0, e1);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[c * 16 + i] = 0u;
-                }
-            }
-            const float lsum = l0 + l1;
-            l_run += lsum;
-            m_run = m_new;
-            tc_fence_before();
-            mbar_arrive(s_free);                        // S(j) fully consumed: QK(j+1) may overwrite it
-            // ---- wait for PV(j-1): P buffer free, O stable ----
+            // ---- PV(j-1) complete: the P buffer is free and O is stable; rescale O in place if some row maximum grew ----
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);
                 tc_fence_after();
@@ -417,18 +415,37 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                     tmem_st_wait();
                 }
             }
-            // ---- write P (bf16) into the 128B-swizzled K-major layout expected by the PV MMA ----
+            // ---- pass 2: probabilities, written straight into the 128B-swizzled K-major P tile of the PV MMA ----
+            float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int c = 0; c < AT_BN / 32; ++c) {
+                if ((anyc >> c) & 1u) {
+                    uint32_t v[32];
+                    tmem_ld32(t_s + c * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const int w = h * 32 + ch * 4;
-                    uint4 val = make_uint4(pk[w], pk[w + 1], pk[w + 2], pk[w + 3]);
-                    *reinterpret_cast<uint4*>(p_row + h * (AT_BM * 128) + ((ch ^ (r & 7)) << 4)) = val;
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float e0 = fast_exp2(__fmaf_rn(__uint_as_float(v[g * 8 + 2 * i]), p.scale_log2, -m_use));
+                            const float e1 = fast_exp2(__fmaf_rn(__uint_as_float(v[g * 8 + 2 * i + 1]), p.scale_log2, -m_use));
+                            l0 += e0;
+                            l1 += e1;
+                            w[i] = pack_bf16(e0, e1);
+                        }
+                        *reinterpret_cast<uint4*>(p_row + (((c * 4 + g) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(p_row + (((c * 4 + g) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
+            l_run += l0 + l1;
+            m_run = m_new;
             fence_proxy_async();
             tc_fence_before();
+            mbar_arrive(&s_free[j % AT_S_BUFS]);        // S(j) fully consumed: QK(j + bufs) may overwrite this buffer
             mbar_arrive(p_full);
         }
         // ---- epilogue: O / l -> bf16 -> global ----
@@ -472,7 +489,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// Epipolar tile map: bit (q_tile, k_tile) = "some query of the 128-query tile may see some key of the 128-key tile".
+// Epipolar tile map: bit (q_tile, k_tile) = "some query of the 128-query tile may see some key of the 64-key tile".
 // Same conservative per-image-row interval test (and the same rounding margin) as the in-tile row skip of attn_tc_kernel,
 // so a cleared bit implies every chunk of that tile would have been skipped anyway: results are bit-identical with and
 // without the map.  F is constant over the 25 steps x 2 passes x 16 layers of a sample, so the map is built once per sample.
@@ -552,6 +569,7 @@ static int launch_attn(const AttnKernelArgs& a, int q_tiles, int heads, int batc
 }
 
 int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
+    if ((a.lk + AT_BN - 1) / AT_BN + (a.lk2 > 0 ? 1 : 0) > AT_MAX_TILES || a.lk2 > AT_BN) return ERR_UNSUPPORTED;
     if (a.epi_F && a.epi_H == a.epi_W && a.lk % AT_BN == 0) {
         const int w = a.epi_W, d = a.epi_d;
         if (w == 32 && d == 8) return launch_attn<5, 8>(a, q_tiles, heads, batch, st);

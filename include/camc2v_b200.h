@@ -101,7 +101,7 @@ int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* o
  * q: [bq, lq, heads*64] (row stride ldq elements), k/v: [bk, lk, heads*64] (strides ldk/ldv); query batch b uses
  * kv batch b / kv_div (context broadcast over frames).  out: [bq, lq, heads*64] (stride ldo).
  * accumulate != 0: out = out + out_scale * result (image cross-attention sum, attention.py:140-144).
- * k2/v2 (optional, lk2 <= 128 rows, [lk2, heads*64], shared by every batch): an extra, never-masked key
+ * k2/v2 (optional, lk2 <= 64 rows, [lk2, heads*64], shared by every batch): an extra, never-masked key
  *   segment — the epipolar register tokens (epipolar.py:86-96; softmax is invariant to key order, so they
  *   are appended instead of prepended).
  * Masking of the main segment, at most one of:
@@ -134,7 +134,7 @@ int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int
  * ---------------------------------------------------------------------------------------------- */
 /* Materialise the epipolar mask (camcontexti2v.py:202-271): F fp32 [B,T,T,3,3] -> uint8 [B, T*H*W, T*H*W]. Bit-exact. */
 int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, int d, void* stream);
-/* Conservative tile-occupancy bitmap of the epipolar mask for 128x128 (query, key) tiles of a square power-of-two grid
+/* Conservative tile-occupancy bitmap of the epipolar mask for 128x64 (query, key) tiles of a square power-of-two grid
  * (W in {8,16,32}): map[b][q_tile][word] bit j = key tile j may contain an attended pair.  Words per row =
  * c2v_epipolar_tile_map_words(T,H,W).  Returns 4 (unsupported) for other grids: callers then simply pass no map. */
 int c2v_epipolar_tile_map(const float* F, uint32_t* map, int B, int T, int H, int W, int d, void* stream);

@@ -231,11 +231,11 @@ def test_attention_epipolar(T, H, W, d, heads, kind):
         out_t = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm.to(DEV).contiguous(), epi_grid=(T, H, W),
                               epi_d=d, epi_tile_map=tmap)
         assert torch.equal(out, out_t)
-        nt = (L + 127) // 128
-        bits = torch.tensor([[(int(tmap[0, qt, j >> 5]) >> (j & 31)) & 1 for j in range(nt)] for qt in range(nt)], dtype=torch.bool)
-        mpad = torch.zeros(nt * 128, nt * 128, dtype=torch.bool)
+        nt, nk = (L + 127) // 128, (L + 63) // 64          # 128-query x 64-key tiles
+        bits = torch.tensor([[(int(tmap[0, qt, j >> 5]) >> (j & 31)) & 1 for j in range(nk)] for qt in range(nt)], dtype=torch.bool)
+        mpad = torch.zeros(nt * 128, nk * 64, dtype=torch.bool)
         mpad[:L, :L] = mask[0].cpu()
-        occ = mpad.view(nt, 128, nt, 128).any(dim=3).any(dim=1)
+        occ = mpad.view(nt, 128, nk, 64).any(dim=3).any(dim=1)
         assert bool((bits | ~occ).all()), "tile map cleared a tile that contains an attended pair"
         print(f"tile map {kind} {H}x{W}: {bits.float().mean():.3f} of tiles visited, {occ.float().mean():.3f} truly occupied")
 
