@@ -213,22 +213,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): 1 RCP + 1 EX2 + 8 FMA-class ops instead of libdevice erff.
-// Used where the result is rounded to bf16 anyway (GEGLU gate, attention.py:437-438).
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
+// x * gelu_erf(g) with erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): 1 RCP + 1 EX2 + 12 FMA-class ops instead of
+// libdevice erff.  Used where the result is rounded to bf16 anyway (GEGLU gate, attention.py:437-438).
+//   z = |g|/sqrt2, t = 1/(1 + p z), erf|.| = 1 - poly(t) exp(-z^2);  x*gelu(g) = h + h*erf(g) with h = 0.5*g*x
+__device__ __forceinline__ float geglu_fast(float x, float g) {
     float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(g), 1.0f)));
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
     poly *= t;
-    const float e = fast_exp2(-z * z * 1.4426950408889634f);
-    const float erf_abs = fmaf(-poly, e, 1.0f);
-    const float erfv = copysignf(erf_abs, x);
-    return 0.5f * x * (1.0f + erfv);
+    const float e = fast_exp2((g * g) * (-0.5f * 1.4426950408889634f));
+    const float erfv = copysignf(fmaf(-poly, e, 1.0f), g);
+    const float h = (0.5f * g) * x;
+    return fmaf(h, erfv, h);
 }
+__device__ __forceinline__ float gelu_erf_fast(float g) { return geglu_fast(1.0f, g); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);

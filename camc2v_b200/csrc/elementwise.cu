@@ -176,18 +176,37 @@ int copy_rows_launch(const void* src, void* dst, int rows, int C, int B, int64_t
 // small-M linear: one warp per output feature, weights streamed once (bf16, 16-byte loads)
 // ------------------------------------------------------------------------------------------------
 constexpr int SK_MAXM = 8;
+constexpr int SK_SMEM_FLOATS = 12288;   // 48 KB of staged activations per CTA
+// Activations (after the optional SiLU) are staged once per CTA in shared memory; every warp then streams one weight row
+// with all of its 16-byte loads in flight and reduces over K with shuffles.
 __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ out, int M, int N, int K,
-                                                            int silu_in) {
+                                                            int silu_in, int mb) {
+    extern __shared__ float xs[];           // [mb][K]
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (n >= N) return;
     const int lane = threadIdx.x & 31;
-    for (int m0 = 0; m0 < M; m0 += SK_MAXM) {
+    for (int m0 = 0; m0 < M; m0 += mb) {
+        const int mc = min(mb, M - m0);
+        __syncthreads();
+        for (int i = threadIdx.x * 4; i < mc * K; i += blockDim.x * 4) {
+            float4 x = *reinterpret_cast<const float4*>(in + (size_t)m0 * K + i);
+            if (silu_in) {
+                x.x = x.x / (1.0f + expf(-x.x));
+                x.y = x.y / (1.0f + expf(-x.y));
+                x.z = x.z / (1.0f + expf(-x.z));
+                x.w = x.w / (1.0f + expf(-x.w));
+            }
+            *reinterpret_cast<float4*>(xs + i) = x;
+        }
+        __syncthreads();
+        if (n >= N) continue;
         float acc[SK_MAXM];
 #pragma unroll
         for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
+        const __nv_bfloat16* wr = w + (size_t)n * K;
+#pragma unroll 4
         for (int k = lane * 8; k < K; k += 256) {
-            const uint4 wv = *reinterpret_cast<const uint4*>(w + (size_t)n * K + k);
+            const uint4 wv = *reinterpret_cast<const uint4*>(wr + k);
             const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wv);
             float wf[8];
 #pragma unroll
@@ -197,28 +216,37 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
             }
 #pragma unroll
             for (int m = 0; m < SK_MAXM; ++m) {
-                if (m0 + m < M) {
-                    const float* xr = in + (size_t)(m0 + m) * K + k;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float xv = xr[e];
-                        if (silu_in) xv = xv / (1.0f + expf(-xv));
-                        acc[m] = fmaf(xv, wf[e], acc[m]);
-                    }
+                if (m < mc) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(xs + m * K + k);
+                    const float4 x1 = *reinterpret_cast<const float4*>(xs + m * K + k + 4);
+                    acc[m] = fmaf(x0.x, wf[0], acc[m]);
+                    acc[m] = fmaf(x0.y, wf[1], acc[m]);
+                    acc[m] = fmaf(x0.z, wf[2], acc[m]);
+                    acc[m] = fmaf(x0.w, wf[3], acc[m]);
+                    acc[m] = fmaf(x1.x, wf[4], acc[m]);
+                    acc[m] = fmaf(x1.y, wf[5], acc[m]);
+                    acc[m] = fmaf(x1.z, wf[6], acc[m]);
+                    acc[m] = fmaf(x1.w, wf[7], acc[m]);
                 }
             }
         }
 #pragma unroll
         for (int m = 0; m < SK_MAXM; ++m) {
-            const float s = warp_sum(acc[m]);
-            if (lane == 0 && m0 + m < M) out[(size_t)(m0 + m) * N + n] = s + (bias ? bias[n] : 0.f);
+            if (m < mc) {                                   // warp-uniform
+                const float s = warp_sum(acc[m]);
+                if (lane == 0) out[(size_t)(m0 + m) * N + n] = s + (bias ? bias[n] : 0.f);
+            }
         }
     }
 }
 
 int skinny_linear_launch(const float* in, const void* w, const float* bias, float* out, int M, int N, int K, int silu_in, cudaStream_t st) {
-    if (K % 8) return ERR_UNSUPPORTED;
-    skinny_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(in, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N, K, silu_in);
+    if (K % 8 || K > SK_SMEM_FLOATS) return ERR_UNSUPPORTED;
+    int mb = SK_SMEM_FLOATS / K;
+    if (mb > SK_MAXM) mb = SK_MAXM;
+    if (mb > M) mb = M;
+    skinny_linear_kernel<<<(N + 7) / 8, 256, (size_t)mb * K * sizeof(float), st>>>(in, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N,
+                                                                                  K, silu_in, mb);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -22,7 +22,8 @@ namespace c2v {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 3;
+constexpr int MIN_STAGES = 3;    // the TMA epilogue stages BN/32 x 16 KB chunks in the idle pipeline buffers
+constexpr int MAX_STAGES = 8;
 constexpr int GEMM_THREADS = 192;
 
 template <int BN>
@@ -30,8 +31,7 @@ struct GemmSmem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers/tmem ptr + 1024B alignment slack
+    static constexpr int total(int stages) { return stages * STAGE_BYTES + 256 + 1024; }  // + barriers/tmem ptr + 1024B alignment slack
 };
 
 template <int BN>
@@ -39,9 +39,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     using S = GemmSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_bar = empty_bar + STAGES;
+    const int STAGES = p.stages;                          // smem ring depth chosen per launch (gemm_tc_launch)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* acc_bar = empty_bar + MAX_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_bar + 1);
     uint64_t* res_bar = acc_bar + 2;                      // [BN / 32] residual-chunk arrival barriers (TMA epilogue)
 
@@ -98,6 +99,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                 c1 = m0 % p.dim1;
             }
             const uint32_t tx = (uint32_t)p.tile_rows * BK * 2 + S::B_BYTES;
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
                 const int git = it_begin + it;
                 const int tap = git / p.k_chunks, kc = git - tap * p.k_chunks;
@@ -110,8 +113,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                         d2 = tap - 1;
                     }
                 }
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait<100>(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * S::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + S::A_BYTES;
@@ -121,14 +122,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                 else
                     tma_load_4d(a_dst, &p.tmA, &full_bar[s], kc * BK, c1 + d1, c2 + d2, c3);
                 tma_load_2d(b_dst, &p.tmB, &full_bar[s], git * BK, n0);
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
             mbar_wait<20>(&full_bar[s], ph);
             tc_fence_after();
             if (elect_one()) {
@@ -145,6 +150,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                 if (it == iters - 1) umma_commit(acc_bar);
             }
             __syncwarp();
+            if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
+            }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -167,44 +176,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             const bool leader = threadIdx.x == 64;      // warp 2, lane 0: owns the bulk async-group of the stores
             mbar_wait<200>(acc_bar, 0);                 // every MMA has completed: accumulator valid, smem stages free
             tc_fence_after();
-            if (p.epi == EPI_GEGLU) {
-                // x * gelu(gate): value columns [0, BN/2) and gate columns [BN/2, BN) of this tile; bf16 result staged per
-                // 16-column chunk (32-byte rows) and written by TMA stores
-                constexpr int HALF = BN / 2;
-                const int no = blockIdx.y * HALF;
-#pragma unroll 1
-                for (int c = 0; c < HALF; c += 16) {
-                    uint32_t xv[16], gv[16];
-                    tmem_ld16(trow + c, xv);
-                    tmem_ld16(trow + HALF + c, gv);
-                    tmem_ld_wait();
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
-                        float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
-                        if (p.bias) {
-                            x0 += p.bias[n0 + c + j];
-                            x1 += p.bias[n0 + c + j + 1];
-                            g0 += p.bias[n0 + HALF + c + j];
-                            g1 += p.bias[n0 + HALF + c + j + 1];
-                        }
-                        pk[j / 2] = pack_bf16(x0 * gelu_erf_fast(g0), x1 * gelu_erf_fast(g1));
-                    }
-                    uint8_t* buf = smem + (c >> 4) * 4096;
-                    uint4* dst = reinterpret_cast<uint4*>(buf + r * 32);
-                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    fence_proxy_async();
-                    named_bar_sync(1, 128);
-                    if (leader) {
-                        tma_store_3d(&p.tmO, buf, no + c, m0, 0);
-                        tma_store_commit();
-                    }
-                }
-                if (leader) tma_store_wait_read_all();
-                tc_fence_before();
-            } else {
+            {
             if (leader && has_res) {
                 for (int c = 0; c < NCH; ++c) {
                     if (n0 + c * 32 >= p.N) break;
@@ -212,6 +184,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                     tma_load_2d(smem + c * 16384, &p.tmR, &res_bar[c], n0 + c * 32, m0);
                 }
             }
+#ifndef C2V_EPI_FLUSH
+#define C2V_EPI_FLUSH 3
+#endif
+            const int flush = (!out_f32 && has_res) ? 1 : C2V_EPI_FLUSH;
+            int c_flushed = 0;
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 if (n0 + c * 32 >= p.N) break;          // CTA-uniform
@@ -240,7 +217,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                             f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                         }
                     } else {
-                        for (int j = 0; j < 32; ++j)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)                  // static indices: f[] must stay in registers
                             if (nb + j < p.N) f[j] += bias[nb + j];
                     }
                 }
@@ -264,11 +242,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                             make_uint4(pack_bf16(f[8 * k], f[8 * k + 1]), pack_bf16(f[8 * k + 2], f[8 * k + 3]),
                                        pack_bf16(f[8 * k + 4], f[8 * k + 5]), pack_bf16(f[8 * k + 6], f[8 * k + 7]));
                 }
-                fence_proxy_async();
-                named_bar_sync(1, 128);
-                if (leader) {
-                    tma_store_3d(&p.tmO, buf, nb, m0, blockIdx.z);
-                    tma_store_commit();
+                // Hand finished chunks to the TMA store engine.  Each hand-over costs a proxy fence + a 128-thread barrier, so
+                // chunks are flushed in batches of `flush` (per chunk only when bf16 rows alias other threads' residual rows).
+                const bool last = (c + 1 == NCH) || (n0 + (c + 1) * 32 >= p.N);
+                if (c + 1 - c_flushed >= flush || last) {
+                    fence_proxy_async();
+                    named_bar_sync(1, 128);
+                    if (leader) {
+                        for (int cf = c_flushed; cf <= c; ++cf) tma_store_3d(&p.tmO, smem + cf * 16384, n0 + cf * 32, m0, blockIdx.z);
+                        tma_store_commit();
+                    }
+                    c_flushed = c + 1;
                 }
             }
             if (leader) tma_store_wait_read_all();
@@ -290,21 +274,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                 uint32_t xv[16], gv[16];
                 tmem_ld16(trow + c, xv);
                 tmem_ld16(trow + HALF + c, gv);
+                float bx[16], bg[16];                  // bias of the value / gate columns (same for every row: L1 broadcast)
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(p.bias + n0 + c + j);
+                        const float4 g4 = *reinterpret_cast<const float4*>(p.bias + n0 + HALF + c + j);
+                        bx[j] = a4.x; bx[j + 1] = a4.y; bx[j + 2] = a4.z; bx[j + 3] = a4.w;
+                        bg[j] = g4.x; bg[j + 1] = g4.y; bg[j + 2] = g4.z; bg[j + 3] = g4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) bx[j] = bg[j] = 0.f;
+                }
                 tmem_ld_wait();
                 if (row_ok) {
                     uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
-                        float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
-                        if (p.bias) {
-                            x0 += p.bias[n0 + c + j];
-                            x1 += p.bias[n0 + c + j + 1];
-                            g0 += p.bias[n0 + HALF + c + j];
-                            g1 += p.bias[n0 + HALF + c + j + 1];
-                        }
-                        pk[j / 2] = pack_bf16(x0 * gelu_erf_fast(g0), x1 * gelu_erf_fast(g1));
-                    }
+                    for (int j = 0; j < 16; j += 2)
+                        pk[j / 2] = pack_bf16(geglu_fast(__uint_as_float(xv[j]) + bx[j], __uint_as_float(gv[j]) + bg[j]),
+                                              geglu_fast(__uint_as_float(xv[j + 1]) + bx[j + 1], __uint_as_float(gv[j + 1]) + bg[j + 1]));
                     uint4* dst = reinterpret_cast<uint4*>(o + c);
                     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -357,7 +346,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                         }
                     } else {
                         // ragged N tail (e.g. the 4-channel output conv): scalar path
-                        for (int j = 0; j < nvalid; ++j) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {                // static indices: f[] must stay in registers
+                            if (j >= nvalid) break;
                             float x = f[j];
                             const int n = n0 + c + j;
                             if (bias) x += bias[n];
@@ -387,10 +378,22 @@ static int launch(const GemmKernelArgs& a, int m_tiles, int n_tiles, cudaStream_
     using S = GemmSmem<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        C2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        C2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    gemm_tc_kernel<BN><<<dim3(m_tiles, n_tiles, a.splits), GEMM_THREADS, S::TOTAL, st>>>(a);
+    // Ring depth: a grid that puts at most one CTA on an SM has the whole 227 KB to itself and is latency-bound on the
+    // K loop (few tiles, deep K: the 16x16 / 8x8 / 4x4 levels), so it gets as many stages as fit; otherwise stay within
+    // half an SM so that two CTAs are co-resident and one's epilogue overlaps the other's main loop.
+    GemmKernelArgs b = a;
+    const int ctas = m_tiles * n_tiles * a.splits;
+    const int budget = (ctas <= 148 ? 227 : 113) * 1024 - 1024;      // 1 KB per CTA is reserved by the system
+    int stages = (budget - 256 - 1024) / S::STAGE_BYTES;
+    const int iters = (a.taps * a.k_chunks + a.splits - 1) / a.splits;
+    if (stages > iters) stages = iters;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < MIN_STAGES) stages = MIN_STAGES;
+    b.stages = stages;
+    gemm_tc_kernel<BN><<<dim3(m_tiles, n_tiles, a.splits), GEMM_THREADS, S::total(stages), st>>>(b);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -29,6 +29,7 @@ struct GemmKernelArgs {
     void* out;              // fp32 or bf16 [M, ldo]
     int ldo;
     int out_bf16;
+    int stages;             // smem ring depth (set by gemm_tc_launch)
     int splits;             // split-K factor (grid.z); > 1: raw fp32 partials go to `out` = ws[z][M][N]
 };
 
