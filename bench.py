@@ -300,6 +300,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--serial-passes", action="store_true", help="do not overlap the cond / uncond UNet passes inside the CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg-split", action="store_true",
+                    help="latency mode: ranks (2k, 2k+1) share the videos of pair k, one runs the cond pass, the other the uncond pass")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -322,7 +324,15 @@ def main():
     peaks = measured_peaks()
     cfg = UNetConfig()
     B = args.batch
-    model, sampler, host, cam_host, _ = build_workload(cfg, B, device, seed_offset=rank)
+    pair = None
+    if args.cfg_split:
+        if world < 2 or world % 2:
+            raise SystemExit("--cfg-split needs an even number of ranks (torchrun --nproc-per-node 2/4/8)")
+        from camc2v_b200.parallel import make_cfg_pairs
+        pair = make_cfg_pairs(rank, world)
+    units = world // 2 if pair is not None else world          # independent video streams of the job
+    model, sampler, host, cam_host, _ = build_workload(cfg, B, device, seed_offset=(rank // 2 if pair is not None else rank))
+    sampler.cfg_pair = pair
     for k in ("x", "c_concat", "ctx_cond", "ctx_uncond"):
         host[k] = pin(host[k])
     host["pluker"] = [pin(p) for p in host["pluker"]]
@@ -355,14 +365,15 @@ def main():
     if not args.no_graph and sampler._graph is not None:
         # kernels inside the captured graph are replayed once per step
         n0 = _lib.LAUNCHES
-        model.apply_model(sampler._graph["x"], sampler._graph["t"], cond, fs=static["fs"], enable_camera_condition=True)
-        model.apply_model(sampler._graph["x"], sampler._graph["t"], uc, fs=static["fs"], enable_camera_condition=True)
+        if pair is None or pair.role == 0:
+            model.apply_model(sampler._graph["x"], sampler._graph["t"], cond, fs=static["fs"], enable_camera_condition=True)
+        if pair is None or pair.role == 1:
+            model.apply_model(sampler._graph["x"], sampler._graph["t"], uc, fs=static["fs"], enable_camera_condition=True)
         graph_kernels = _lib.LAUNCHES - n0
         barrier()
         launches0 = _lib.LAUNCHES
     clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    clocks.start()                      # every rank samples its own GPU; rank 0 reports its own and the job-wide minimum
     x = host["x"].to(device)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -372,14 +383,20 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop()
     eager_kernels = _lib.LAUNCHES - launches0
     gpu_launches = eager_kernels + graph_kernels * args.steps
     tms = torch.tensor([ms], device=device)
+    per_rank_ms, per_rank_mhz = [ms / args.steps], [float(clk.get("sm_mhz") or 0.0)]
     if world > 1:
+        stats = torch.tensor([ms / args.steps, per_rank_mhz[0]], device=device)
+        allst = [torch.empty_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+        per_rank_ms = [float(t[0]) for t in allst]
+        per_rank_mhz = [float(t[1]) for t in allst]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
-    value = args.steps * B * world / (ms * 1e-3)  # video-steps per second: one step advances B videos per GPU by one DDIM step
+    value = args.steps * B * units / (ms * 1e-3)  # video-steps per second: one step advances B videos per GPU by one DDIM step
     finite = bool(torch.isfinite(x).all())
 
     # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
@@ -405,7 +422,7 @@ def main():
     te = torch.tensor([e2e_s], device=device)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = args.steps * B * world / float(te.item())
+    e2e_value = args.steps * B * units / float(te.item())
 
     # the north star's only collective: gather the final latents over NVLink
     if world > 1:
@@ -422,9 +439,14 @@ def main():
                 "videos_per_s": value / steps_per_video,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": int(gpu_launches), "clocks": clk, "finite": finite,
+                "per_rank": {"ms_per_step": per_rank_ms, "sm_mhz": per_rank_mhz},
                 "step_roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": sustained, "unit": "TFLOP/s",
                                   "frac": per_gpu_tflops / sustained, "flops_per_step": step_flops,
                                   "peak_source": f"{peaks[1]} sustained bf16 (whole step)"}}
+        if pair is not None:
+            line["config"]["parallelism"] = (f"cfg-split: {units} rank pairs, cond pass on even / uncond pass on odd ranks, one 2-rank "
+                                             "NCCL all_gather of the noise predictions per step (latency mode)")
+            line["config"]["global_batch"] = B * units
         try:
             line["roofline"] = time_dominant_kernel(device, peaks)
         except Exception as e:  # the bench line must still be printed

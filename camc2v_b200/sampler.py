@@ -91,6 +91,7 @@ class DDIMSampler(object):
         self.schedule = schedule
         self._graph = None
         self.concurrent_passes = kwargs.get("concurrent_passes", True)
+        self.cfg_pair = kwargs.get("cfg_pair", None)       # parallel.CfgPair: split the CFG halves over two ranks
 
     # -------------------------------------------------------------------------------------------- schedule
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
@@ -150,40 +151,48 @@ class DDIMSampler(object):
         return img, intermediates
 
     # -------------------------------------------------------------------------------------------- one step
-    def _unet_pair(self, x, t, c, uc, kwargs, use_cuda_graph):
-        """The two apply_model calls of a CFG step (ddim.py:262-263), optionally replayed from one CUDA graph."""
+    def _unet_passes(self, x, t, conds, kwargs, use_cuda_graph):
+        """apply_model for every conditioning in `conds` (the cond / uncond passes of a CFG step, ddim.py:262-263, or just
+        one of them under CFG-split), optionally replayed from one CUDA graph with the passes as parallel branches."""
         if not use_cuda_graph:
-            return self.model.apply_model(x, t, c, **kwargs), self.model.apply_model(x, t, uc, **kwargs)
+            return [self.model.apply_model(x, t, c, **kwargs) for c in conds]
         g = self._graph
-        key = (id(c), id(uc), tuple(x.shape))
+        key = (tuple(id(c) for c in conds), tuple(x.shape))
         if g is None or g["key"] != key:
             sx, st = x.clone(), t.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):          # warm-up outside capture: builds weight packs, fills allocator pools
-                self.model.apply_model(sx, st, c, **kwargs)
-                self.model.apply_model(sx, st, uc, **kwargs)
+                for c in conds:
+                    self.model.apply_model(sx, st, c, **kwargs)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                # The cond and uncond passes are independent: capture them as two parallel branches of the graph so that
+                # The cond and uncond passes are independent: capture them as parallel branches of the graph so that
                 # the small grids of the 8x8 / 4x4 levels and every kernel's last partial wave overlap with the other pass.
                 main = torch.cuda.current_stream()
-                if self.concurrent_passes:
-                    side2 = torch.cuda.Stream()
-                    side2.wait_stream(main)
-                    ec = self.model.apply_model(sx, st, c, **kwargs)
-                    with torch.cuda.stream(side2):
-                        eu = self.model.apply_model(sx, st, uc, **kwargs)
-                    main.wait_stream(side2)
-                else:
-                    ec = self.model.apply_model(sx, st, c, **kwargs)
-                    eu = self.model.apply_model(sx, st, uc, **kwargs)
-            g = self._graph = dict(key=key, graph=graph, x=sx, t=st, ec=ec, eu=eu)
+                outs = [self.model.apply_model(sx, st, conds[0], **kwargs)]
+                branches = []
+                for c in conds[1:]:
+                    if self.concurrent_passes:
+                        br = torch.cuda.Stream()
+                        br.wait_stream(main)
+                        with torch.cuda.stream(br):
+                            outs.append(self.model.apply_model(sx, st, c, **kwargs))
+                        branches.append(br)
+                    else:
+                        outs.append(self.model.apply_model(sx, st, c, **kwargs))
+                for br in branches:
+                    main.wait_stream(br)
+            g = self._graph = dict(key=key, graph=graph, x=sx, t=st, outs=outs, ec=outs[0], eu=outs[-1])
         g["x"].copy_(x)
         g["t"].copy_(t)
         g["graph"].replay()
-        return g["ec"], g["eu"]
+        return g["outs"]
+
+    def _unet_pair(self, x, t, c, uc, kwargs, use_cuda_graph):
+        ec, eu = self._unet_passes(x, t, [c, uc], kwargs, use_cuda_graph)
+        return ec, eu
 
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
@@ -212,7 +221,14 @@ class DDIMSampler(object):
                 cam = c.get("camera_condition")
                 if cam is not None and uc.get("camera_condition") is not cam:
                     uc["camera_condition"] = cam
-            e_c, e_u = self._unet_pair(x, t, c, uc, kwargs, use_cuda_graph)
+            if self.cfg_pair is not None:
+                # CFG-split (parallel.CfgPair): this rank runs ONE of the two passes, the pair exchanges the predictions
+                e_loc = self._unet_passes(x, t, [c if self.cfg_pair.role == 0 else uc], kwargs, use_cuda_graph)[0]
+                e_c, e_u = self.cfg_pair.exchange(e_loc)
+                if noise is None:
+                    noise = self.cfg_pair.noise(x.shape, x.device)
+            else:
+                e_c, e_u = self._unet_pair(x, t, c, uc, kwargs, use_cuda_graph)
             scale, phi = float(unconditional_guidance_scale), float(guidance_rescale)
         if noise is None:
             noise = torch.randn(x.shape, device=x.device)

@@ -183,6 +183,21 @@ def test_flop_model_matches_reference_counts():
 
 
 # ------------------------------------------------------------------------------------------------ multi-GPU host logic (gloo)
+def _run_world(code: str, nproc: int, port: int):
+    import tempfile
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(code)
+        path = f.name
+    try:
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+                            "127.0.0.1", "--master-port", str(port), path], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("ok") == nproc
+    finally:
+        os.remove(path)
+
+
 def test_video_sharding_and_latent_gather_world2():
     """N > 1 path of bench.py / parallel.py: videos[rank::world] sharding, no step-time collective, one all_gather of the
     final latents — exercised with 2 gloo ranks on CPU."""
@@ -202,19 +217,36 @@ if rank == 0:
     assert [int(allv[i, 0, 0, 0, 0]) for i in range(7)] == vids
 print("ok", rank)
 ''' % ROOT
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", "-c", code] if False else
-                       [sys.executable, "-c", "import sys; sys.exit(0)"], env=env)
-    # torchrun cannot take -c; write the script to a temp file instead
-    import tempfile
-    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
-        f.write(code)
-        path = f.name
-    try:
-        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                            "--master-port", "29533", path], env=env, capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, r.stdout + r.stderr
-        assert r.stdout.count("ok") == 2
-    finally:
-        os.remove(path)
+    _run_world(code, 2, 29533)
+
+
+def test_cfg_split_pair_exchange_world2():
+    """CFG halves on a pair of ranks (parallel.CfgPair, BASELINE config 4): role 0 = cond, role 1 = uncond; after one
+    2-rank all_gather both ranks hold (e_cond, e_uncond); both draw the same eta-noise; both see the pair's videos; the
+    reference's update (oracle.ddim_oracle.cfg_ddim_update) then gives bit-identical latents on the two ranks."""
+    code = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from camc2v_b200 import parallel
+from oracle import ddim_oracle
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+pair = parallel.make_cfg_pairs(rank, world)
+assert pair.role == rank %% 2 and pair.pair_id == 0 and pair.n_pairs == 1
+assert parallel.shard_videos_cfg_split(list(range(5)), rank, world) == list(range(5))
+g = torch.Generator().manual_seed(7)
+x = torch.randn(1, 4, 2, 4, 4, generator=g)
+e_true = [torch.randn(1, 4, 2, 4, 4, generator=g) for _ in range(2)]       # what the cond / uncond pass would return
+e_c, e_u = pair.exchange(e_true[pair.role].clone())
+assert torch.equal(e_c, e_true[0]) and torch.equal(e_u, e_true[1])
+n1, n2 = pair.noise(x.shape, torch.device("cpu")), pair.noise(x.shape, torch.device("cpu"))
+assert not torch.equal(n1, n2)
+s = ddim_oracle.ddim_schedule()
+xp, _ = ddim_oracle.cfg_ddim_update(x, e_c, e_u, n1, float(s["alphas"][3]), float(s["alphas_prev"][3]), float(s["sigmas"][3]),
+                                    float(s["sqrt_one_minus_alphas"][3]), 3.5, 0.7)
+both = [torch.empty_like(xp) for _ in range(2)]
+dist.all_gather(both, xp)
+assert torch.equal(both[0], both[1]), "the two ranks of a pair must stay bit-identical"
+print("ok", rank)
+''' % ROOT
+    _run_world(code, 2, 29534)
