@@ -171,15 +171,17 @@ class DDIMSampler(object):
                 # The cond and uncond passes are independent: capture them as parallel branches of the graph so that
                 # the small grids of the 8x8 / 4x4 levels and every kernel's last partial wave overlap with the other pass.
                 main = torch.cuda.current_stream()
-                outs = [self.model.apply_model(sx, st, conds[0], **kwargs)]
                 branches = []
-                for c in conds[1:]:
-                    if self.concurrent_passes:
-                        br = torch.cuda.Stream()
+                if self.concurrent_passes:
+                    for _ in conds[1:]:               # fork BEFORE anything is captured on main: the branches have no
+                        br = torch.cuda.Stream()      # dependency on the first pass
                         br.wait_stream(main)
-                        with torch.cuda.stream(br):
-                            outs.append(self.model.apply_model(sx, st, c, **kwargs))
                         branches.append(br)
+                outs = [self.model.apply_model(sx, st, conds[0], **kwargs)]
+                for i, c in enumerate(conds[1:]):
+                    if self.concurrent_passes:
+                        with torch.cuda.stream(branches[i]):
+                            outs.append(self.model.apply_model(sx, st, c, **kwargs))
                     else:
                         outs.append(self.model.apply_model(sx, st, c, **kwargs))
                 for br in branches:
