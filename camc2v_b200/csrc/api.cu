@@ -29,6 +29,9 @@ const char* c2v_status_string(int s) {
 int c2v_gemm_tile_n(int N, int epi) {
     if (epi == C2V_EPI_GEGLU) {
         // both halves (value | gate) of an output-column block live in one N tile
+        // these short-K GEMMs are bound by L2 -> smem operand traffic: the widest tile has the highest FLOP per loaded byte
+        // (the 32x32-level FF and init_attn; at the deeper levels M is small and the 2-stage ring of a 256-wide tile starves)
+        if (N % 256 == 0 && N <= 4096) return 256;
         if (N % 160 == 0) return 160;
         if (N % 128 == 0) return 128;
         if (N % 64 == 0) return 64;

@@ -391,7 +391,8 @@ static int launch(const GemmKernelArgs& a, int m_tiles, int n_tiles, cudaStream_
     const int iters = (a.taps * a.k_chunks + a.splits - 1) / a.splits;
     if (stages > iters) stages = iters;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages < MIN_STAGES) stages = MIN_STAGES;
+    const int min_stages = a.epi == EPI_GEGLU ? 2 : MIN_STAGES;       // the GEGLU epilogue stores straight from registers
+    if (stages < min_stages) stages = min_stages;
     b.stages = stages;
     gemm_tc_kernel<BN><<<dim3(m_tiles, n_tiles, a.splits), GEMM_THREADS, S::total(stages), st>>>(b);
     C2V_CHECK_CUDA(cudaGetLastError());

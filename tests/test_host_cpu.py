@@ -36,7 +36,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert loaded.c2v_abi_version() == 1
     assert loaded.c2v_status_string(4) == b"unsupported shape"
     assert loaded.c2v_gemm_tile_n(320, 0) == 160 and loaded.c2v_gemm_tile_n(512, 0) == 128 and loaded.c2v_gemm_tile_n(4, 0) == 64
-    assert loaded.c2v_gemm_tile_n(2560, 1) == 160 and loaded.c2v_gemm_tile_n(4096, 1) == 128
+    assert loaded.c2v_gemm_tile_n(2560, 1) == 256 and loaded.c2v_gemm_tile_n(4096, 1) == 256 and loaded.c2v_gemm_tile_n(10240, 1) == 160
 
 
 def test_structs_match_header_layout():
