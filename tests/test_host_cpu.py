@@ -127,8 +127,10 @@ def test_geglu_interleave_is_a_permutation():
     b = torch.arange(2560, dtype=torch.float32)
     w2, b2 = ops.geglu_interleave(w, b)
     assert sorted(b2.tolist()) == b.tolist()
-    assert b2[:80].tolist() == list(range(80)) and b2[80:160].tolist() == list(range(1280, 1360))   # tile 0 = value[0:80] | gate[0:80]
-    assert b2[160:240].tolist() == list(range(80, 160))
+    half = ops.tile_n(2560, ops.EPI_GEGLU) // 2          # value / gate columns per N tile (128 for the 256-wide tile)
+    assert b2[:half].tolist() == list(range(half))       # tile 0 = value[0:half] | gate[0:half]
+    assert b2[half:2 * half].tolist() == list(range(1280, 1280 + half))
+    assert b2[2 * half:3 * half].tolist() == list(range(half, 2 * half))
 
 
 # ------------------------------------------------------------------------------------------------ schedule / camera / flops

@@ -142,6 +142,20 @@ def single(which):
         Fm = camera.fundamental_matrices(K, camera.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))).to(DEV).contiguous()
         fn = lambda: ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], 1, L, L, h, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm,
                                    epi_grid=(T, H, H), epi_d=d)
+    elif which == "epi0map":
+        T, H, d, h = 16, 32, 8, 5
+        L, C = T * H * H, h * 64
+        qkv, reg = rb(L, 3 * C), rb(4, 2 * C)
+        K, w2c = synth.synth_camera("pan_yaw", T=T)
+        torch.manual_seed(123)
+        Fm = camera.fundamental_matrices(K, camera.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))).to(DEV).contiguous()
+        tmap = ops.epipolar_tile_map(Fm, T, H, H, d)
+        fn = lambda: ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], 1, L, L, h, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm,
+                                   epi_grid=(T, H, H), epi_d=d, epi_tile_map=tmap)
+    elif which == "geglu0":
+        a, w, b = rb(16384, 320), rb(2560, 320), rb(2560, dtype=torch.float32)
+        wi, bi = ops.geglu_interleave(w, b)
+        fn = lambda: ops.geglu_linear(a, wi, bi)
     elif which == "attn0":
         q, kv = rb(16 * 1024, 320), rb(16 * 1024, 640)
         fn = lambda: ops.attention(q, kv[:, :320], kv[:, 320:], 16, 1024, 1024, 5)
