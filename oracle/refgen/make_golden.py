@@ -156,6 +156,20 @@ def gen_unet_small(check):
     out.update(step_x_prev=x_prev.numpy(), step_pred_x0=pred_x0.numpy(), step_index=np.int64(index), step_t=np.int64(step))
     np.savez_compressed(os.path.join(GOLD, "unet_small.npz"), **out)
 
+    # the whole 25-step sampling loop of the reference (ddim.py:59-238): x_T given, eta-noise from torch's CPU generator
+    # seeded right before the call (one randn per step, ddim.py:340), CFG 3.5, guidance_rescale 0.7, uniform_trailing
+    import time
+    t0 = time.time()
+    torch.manual_seed(20230211)
+    pred = []
+    samples, _ = sampler.sample(25, 1, tuple(inp["x"].shape[1:]), conditioning=cond, eta=1.0, verbose=False, x_T=inp["x"],
+                                unconditional_guidance_scale=3.5, unconditional_conditioning=uc, fs=inp["fs"],
+                                timestep_spacing="uniform_trailing", guidance_rescale=0.7, enable_camera_condition=True,
+                                img_callback=lambda p0, i: pred.append(p0.clone()))
+    print(f"  25-step reference loop on the small model: {time.time() - t0:.1f} s, final std {samples.std():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "loop_small.npz"), x_final=samples.numpy(), pred_x0_step5=pred[4].numpy(),
+                        pred_x0_step15=pred[14].numpy(), pred_x0_final=pred[-1].numpy(), seed=np.int64(20230211))
+
     if check:
         from oracle.unet_oracle import UNetOracle
         orc = UNetOracle(unet.state_dict(), SMALL_CFG)
