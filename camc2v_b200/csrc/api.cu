@@ -90,8 +90,15 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     a.out_bf16 = d->out_bf16;
     a.splits = d->splitk > 1 ? d->splitk : 1;
     if (a.splits > 1) {
-        if (!d->ws || d->epi != C2V_EPI_LINEAR || a.splits > a.taps * a.k_chunks) return ERR_BAD_ARG;
-        a.out = d->ws;
+        if (d->epi != C2V_EPI_LINEAR || a.splits > a.taps * a.k_chunks) return ERR_BAD_ARG;
+        if (!d->ws) {
+            // no workspace: the splits of a tile run as one thread-block cluster (<= 8 CTAs) and reduce through DSMEM
+            if (a.splits > 8 || d->ldo % 4 != 0 || (d->residual && d->ldr % 4 != 0)) return ERR_UNSUPPORTED;
+            if ((reinterpret_cast<uintptr_t>(d->out) & 15) != 0 && !d->out_bf16) return ERR_UNSUPPORTED;
+            a.cluster_reduce = 1;
+        } else {
+            a.out = d->ws;
+        }
     }
 
     if (d->a_mode == C2V_A_PLAIN) {
@@ -156,7 +163,7 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
         const uint32_t box[2] = {64, (uint32_t)bn};
         if (!make_tmap_bf16(&a.tmB, d->w, 2, dims, strides, box)) return ERR_TMA_ENCODE;
     }
-    if (d->epi == C2V_EPI_LINEAR) {
+    if (d->epi == C2V_EPI_LINEAR && !a.cluster_reduce) {
         // TMA epilogue descriptors (residual load, output / split-K partial store).  When the output rows are not 16-byte
         // aligned (e.g. a 4-column bf16 output) the kernel falls back to its direct-store epilogue.
         const bool part = a.splits > 1;
@@ -187,7 +194,7 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     const int n_tiles = (d->N + bn - 1) / bn;
     if (n_tiles > 65535) return ERR_UNSUPPORTED;
     const int rc = gemm_tc_launch(a, bn, m_tiles, n_tiles, (cudaStream_t)stream);
-    if (rc != OK || a.splits == 1) return rc;
+    if (rc != OK || a.splits == 1 || a.cluster_reduce) return rc;
     return splitk_reduce_launch(d->ws, a.splits, d->M, d->N, d->bias, d->rowbias, a.rows_per_group, d->residual, d->ldr, d->out, d->ldo,
                                 d->out_bf16, (cudaStream_t)stream);
 }

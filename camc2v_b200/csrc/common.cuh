@@ -230,6 +230,17 @@ __device__ __forceinline__ float geglu_fast(float x, float g) {
     return fmaf(h, erfv, h);
 }
 __device__ __forceinline__ float gelu_erf_fast(float g) { return geglu_fast(1.0f, g); }
+// ---- thread-block clusters: barrier + distributed shared memory ----
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cta_smem_addr, uint32_t cta_rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(cta_smem_addr), "r"(cta_rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);

@@ -123,7 +123,7 @@ def by_shape(model, sampler, cond, uc, static, recs):
                    f"sk={max(1, d.splitk)}")
             fl = 2.0 * d.M * d.N * d.Cin * d.taps
             log.append(("gemm_tc", key, fl))
-            if d.splitk > 1:
+            if d.splitk > 1 and d.ws:
                 log.append(("splitk_reduce", f"splitk_reduce M={d.M} N={d.N} sk={d.splitk}", 0.0))
         elif name == "c2v_attention":
             d = a[0]._obj
