@@ -282,7 +282,7 @@ def time_dominant_kernel(device, peaks):
         except Exception:
             traffic = None
     peak = peaks[0]["bf16_tflops"]
-    visited = float(sum(bin(int(w) & 0xffffffff).count("1") for w in tmap.flatten().tolist())) / ((L // 128) * (L // 64))
+    visited = float(sum(bin(int(w) & 0xffffffff).count("1") for w in tmap[..., :-1].flatten().tolist())) / ((L // 128) * (L // 64))
     return {"bound": "tensor", "kernel": "attn_tc_kernel<5,8> (epipolar-masked attention, L=16384 (+4 register keys), 5 heads, d=64; mask evaluated "
                                          f"in-kernel; {visited * 100:.1f}% of the 128x64 (query x key) tiles visited on this trajectory, FLOPs counted dense)",
             "achieved": achieved, "peak": peak, "peak_source": f"{peaks[1]} burst bf16 (kernel timed alone)", "unit": "TFLOP/s",

@@ -99,7 +99,7 @@ def check(status: int, what: str):
         raise C2VError(f"{what} failed: {msg} (status {status})")
 
 
-KERNELS_PER_CALL = {"c2v_groupnorm_silu": 2}   # every other entry point launches exactly one kernel
+KERNELS_PER_CALL = {"c2v_groupnorm_silu": 2, "c2v_epipolar_tile_map": 2}   # every other entry point launches exactly one kernel
 
 
 def call(name: str, *args):

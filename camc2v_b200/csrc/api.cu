@@ -297,7 +297,8 @@ int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, 
     return epipolar_mask_launch(F, out, B, T, H, W, d, (cudaStream_t)stream);
 }
 
-int c2v_epipolar_tile_map_words(int T, int H, int W) { return ((T * H * W + 63) / 64 + 31) / 32; }   // 64-key tiles
+// bitmap words of one query-tile row (64-key tiles) + 1 word holding the longest-first issue order
+int c2v_epipolar_tile_map_words(int T, int H, int W) { return ((T * H * W + 63) / 64 + 31) / 32 + 1; }
 
 int c2v_epipolar_tile_map(const float* F, uint32_t* map, int B, int T, int H, int W, int d, void* stream) {
     if (!F || !map || B <= 0 || B > 65535) return ERR_BAD_ARG;

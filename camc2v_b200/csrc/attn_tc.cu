@@ -110,9 +110,17 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5;
-    const int q0 = blockIdx.x * AT_BM;
-    const int head = blockIdx.y;
+    // CTA -> (query tile, head).  With an epipolar tile map the CTAs are issued heaviest query tile first (longest-processing-
+    // time order, all heads of a tile back to back): the per-tile work varies by 2-3x with the number of key tiles visited and
+    // the grid is only ~2 waves deep, so the hardware's in-order CTA dispatch would otherwise leave a long tail.
     const int b = blockIdx.z;
+    int q_tile = blockIdx.x, head = blockIdx.y;
+    if (p.tile_map) {
+        const int lin = blockIdx.x + gridDim.x * blockIdx.y;
+        head = lin % gridDim.y;
+        q_tile = (int)p.tile_map[((size_t)b * gridDim.x + lin / gridDim.y) * p.tile_map_words + (p.tile_map_words - 1)];
+    }
+    const int q0 = q_tile * AT_BM;
     const int bkv = b / p.kv_div;
     const int n_main = (p.lk + AT_BN - 1) / AT_BN;
     const int n_tiles = n_main + (p.lk2 > 0 ? 1 : 0);       // last tile = register-token segment
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
     uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + AT_OFF_LIST);
     int* n_act_s = reinterpret_cast<int*>(bars + 16);
     if (warp == 2) {
-        const uint32_t* map = p.tile_map ? p.tile_map + ((size_t)b * gridDim.x + blockIdx.x) * p.tile_map_words : nullptr;
+        const uint32_t* map = p.tile_map ? p.tile_map + ((size_t)b * gridDim.x + q_tile) * p.tile_map_words : nullptr;
         int cnt = 0;
         for (int j0 = 0; j0 < n_tiles; j0 += 32) {
             const int j = j0 + lane_id();
@@ -254,6 +262,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
         int cur_t2 = -1;
         EpiLine line = {0.f, 0.f, 0.f};
         float thr_m = 0.f;         // threshold + rounding margin for the conservative row test (fast path)
+        float l0x[FAST ? (1 << LOGW) : 1];   // line.l0 * x_j for the W pixel columns of a key row, refreshed once per key frame
 
         float m_run = -INFINITY;   // running max, already multiplied by scale*log2(e)
         float l_run = 0.f;
@@ -287,6 +296,8 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
                         line = epi_line(Frow + t2 * 9, xi, yi);
                         const float cmax = (float)(W - 1) * DF + OFFC;
                         thr_m = p.epi_thr + 1e-6f + 4e-7f * (fabsf(line.l0) * cmax + fabsf(line.l1) * cmax + fabsf(line.l2));
+#pragma unroll
+                        for (int x = 0; x < W; ++x) l0x[x] = __fmul_rn(line.l0, (float)x * DF + OFFC);   // the FMUL of the predicate
                     }
                     const int py0 = (key0 & (W * W - 1)) >> LOGW;
                     float yr[RPC];
@@ -306,8 +317,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float xj = (float)(i & (W - 1)) * DF + OFFC;      // compile-time constant
-                            const float wv = __fadd_rn(__fmaf_rn(line.l1, yr[i >> LOGW], __fmul_rn(line.l0, xj)), line.l2);
+                            const float wv = __fadd_rn(__fmaf_rn(line.l1, yr[i >> LOGW], l0x[i & (W - 1)]), line.l2);
                             v[i] = fabsf(wv) < p.epi_thr ? v[i] : NEG_INF_BITS;
                         }
                         const float cm = max32(v);
@@ -505,7 +515,7 @@ __global__ void __launch_bounds__(128) epi_tile_map_kernel(const float* __restri
     const int t1 = qi >> (2 * LOGW), pix = qi & (HW - 1);
     const float xi = (float)(pix & (W - 1)) * DF + OFFC, yi = (float)(pix >> LOGW) * DF + OFFC;
     const float* Frow = Fm + ((size_t)b * T + t1) * T * 9;
-    unsigned int* out = map + ((size_t)b * gridDim.x + qt) * words;
+    unsigned int* out = map + ((size_t)b * gridDim.x + qt) * (words + 1);     // last word of a row: LPT order (epi_tile_order_kernel)
     int cur_t2 = -1;
     EpiLine line = {0.f, 0.f, 0.f};
     float thr_m = 0.f;
@@ -538,6 +548,25 @@ __global__ void __launch_bounds__(128) epi_tile_map_kernel(const float* __restri
     }
 }
 
+// order[rank] = query tile with the rank-th largest number of visited key tiles (ties by index); stored in the extra word of
+// row `rank` of the map.  One CTA per batch element, rank sort (n <= 1024 query tiles).
+__global__ void __launch_bounds__(1024) epi_tile_order_kernel(unsigned int* __restrict__ map, int nq, int words) {
+    __shared__ int cnt[1024];
+    unsigned int* m = map + (size_t)blockIdx.x * nq * (words + 1);
+    const int i = threadIdx.x;
+    if (i < nq) {
+        int c = 0;
+        for (int w = 0; w < words; ++w) c += __popc(m[(size_t)i * (words + 1) + w]);
+        cnt[i] = c;
+    }
+    __syncthreads();
+    if (i < nq) {
+        int rank = 0;
+        for (int j = 0; j < nq; ++j) rank += (cnt[j] > cnt[i]) || (cnt[j] == cnt[i] && j < i);
+        m[(size_t)rank * (words + 1) + words] = (unsigned int)i;
+    }
+}
+
 int epi_tile_map_launch(const float* F, unsigned int* map, int B, int T, int H, int W, int d, cudaStream_t st) {
     if (H != W) return ERR_UNSUPPORTED;
     const int L = T * H * W;
@@ -552,6 +581,8 @@ int epi_tile_map_launch(const float* F, unsigned int* map, int B, int T, int H, 
     else if (W == 8 && d == 16) C2V_MAP(3, 16);
     else return ERR_UNSUPPORTED;
 #undef C2V_MAP
+    if (nq > 1024) return ERR_UNSUPPORTED;
+    epi_tile_order_kernel<<<B, 1024, 0, st>>>(map, nq, words);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -140,7 +140,9 @@ int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int
 int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, int d, void* stream);
 /* Conservative tile-occupancy bitmap of the epipolar mask for 128x64 (query, key) tiles of a square power-of-two grid
  * (W in {8,16,32}): map[b][q_tile][word] bit j = key tile j may contain an attended pair.  Words per row =
- * c2v_epipolar_tile_map_words(T,H,W).  Returns 4 (unsupported) for other grids: callers then simply pass no map. */
+ * c2v_epipolar_tile_map_words(T,H,W); the LAST word of row r is not part of the bitmap: it holds the index of the query
+ * tile with the r-th largest number of visited key tiles, and c2v_attention issues its CTAs in that (longest first) order.
+ * Returns 4 (unsupported) for other grids: callers then simply pass no map. */
 int c2v_epipolar_tile_map(const float* F, uint32_t* map, int B, int T, int H, int W, int d, void* stream);
 int c2v_epipolar_tile_map_words(int T, int H, int W);
 /* Pluecker / ray embedding (R/model/base.py:112-174): K fp32 [B,T,3,3], c2w fp32 [B,T,4,4] -> fp32 [B,6,T,H,W]. */
