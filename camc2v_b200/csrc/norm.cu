@@ -180,11 +180,16 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_apply_kernel(const float* __
     }
 }
 
-static int gn_slabs(int ns, int rows, int* rows_per_slab) {
-    // ~2 CTAs per SM in total, but never fewer than 16 rows per CTA (each thread wants several rows in flight)
+static int gn_slabs(int ns, int rows, int C, int* rows_per_slab) {
+    // ~2 CTAs per SM in total, but never fewer than 4 rows per thread (= one unrolled batch of independent 16-byte loads):
+    // the small tensors of the 8x8 / 4x4 levels are latency-bound, so they want many CTAs with ONE round trip each rather
+    // than a few CTAs walking 16 rows serially.
     int target = 296 / (ns > 0 ? ns : 1);
     if (target < 1) target = 1;
-    int slabs = (rows + 15) / 16;
+    const int nvec = C >> 2;
+    const int rows_par = nvec >= GN_THREADS ? 1 : GN_THREADS / nvec;
+    const int min_rows = 4 * rows_par;
+    int slabs = (rows + min_rows - 1) / min_rows;
     if (slabs > target) slabs = target;
     if (slabs < 1) slabs = 1;
     *rows_per_slab = (rows + slabs - 1) / slabs;
@@ -193,7 +198,7 @@ static int gn_slabs(int ns, int rows, int* rows_per_slab) {
 
 int64_t groupnorm_ws_floats(int ns, int rows, int C) {
     int rps;
-    const int slabs = gn_slabs(ns, rows, &rps);
+    const int slabs = gn_slabs(ns, rows, C, &rps);
     return (int64_t)ns * slabs * 64;
 }
 
@@ -202,7 +207,7 @@ int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta,
     if (C % 32 != 0 || C % 4 != 0 || (C >> 2) > GN_THREADS * GN_MAX_SLOTS || ns <= 0 || rows <= 0) return ERR_UNSUPPORTED;
     if (ns > 65535) return ERR_UNSUPPORTED;
     int rps;
-    const int slabs = gn_slabs(ns, rows, &rps);
+    const int slabs = gn_slabs(ns, rows, C, &rps);
     gn_stats_kernel<<<dim3(slabs, ns), GN_THREADS, 0, st>>>(x, ws, rows, C, rps);
     gn_apply_kernel<<<dim3(slabs, ns), GN_THREADS, 0, st>>>(x, ws, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), rows, C, rps, eps, silu);
     C2V_CHECK_CUDA(cudaGetLastError());
