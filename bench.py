@@ -96,21 +96,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def build_workload(cfg: UNetConfig, B: int, device, seed_offset: int = 0):
+def build_workload(cfg: UNetConfig, B: int, device, seed_offset: int = 0, variant: str = "camcontext"):
     from camc2v_b200 import camera
     from camc2v_b200.modules import build_unet
     from camc2v_b200.sampler import DDIMSampler, DenoiserModel
 
-    unet = build_unet(cfg)
+    unet = build_unet(cfg, variant=variant)
     synth.fill_module_(unet, seed=0)
     cpu_sd = None
     model = DenoiserModel(unet).to(device)
     sampler = DDIMSampler(model)
     sampler.make_schedule(25, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
-    host = synth_unet_inputs(cfg, 32, 2, f"bench{seed_offset}", B=B)
+    # CamContextI2V: 1 reference + 2 context frames in the cond context; the baselines (R/baseline/*) have no context frames
+    host = synth_unet_inputs(cfg, 32, 2 if variant == "camcontext" else 0, f"bench{seed_offset}", B=B)
     K, w2c = synth.synth_camera("pan_yaw", T=cfg.temporal_length, B=B)
     torch.manual_seed(123 + seed_offset)
-    cam_host = dict(K=K, w2c=w2c)
+    cam_host = dict(K=K, w2c=w2c, variant=variant)
     return model, sampler, host, cam_host, cpu_sd
 
 
@@ -127,13 +128,18 @@ def to_device_conditioning(host, cam_host, device, static=None):
         B = host["x"].shape[0]
         static["cam"] = camera.camera_condition(cam_host["K"], cam_host["w2c"], torch.zeros(B, dtype=torch.long), 256, 256,
                                                 pluker_embedding_features=static["pluker"], device=device)
+        variant = cam_host.get("variant", "camcontext")
+        if variant == "cameractrl":             # Pluecker features only (cameractrl_modified_modules.py:230-243)
+            static["cam"] = {"pluker_embedding_features": static["pluker"]}
+        elif variant == "motionctrl":           # flattened 3x4 relative poses (motionctrl.py:67-69)
+            static["cam"] = {"RT": static["cam"]["relative_c2w"][:, :, :3, :].reshape(B, -1, 12).to(device).contiguous()}
     for k in ("c_concat", "ctx_cond", "ctx_uncond"):
         static[k].copy_(host[k], non_blocking=True)
         nbytes += host[k].numel() * 4
     for d, s in zip(static["pluker"], host["pluker"]):
         d.copy_(s, non_blocking=True)
         nbytes += s.numel() * 4
-    if nbytes and "cam" in static and static.get("_uploaded"):
+    if nbytes and "epipolar_F" in static.get("cam", {}) and static.get("_uploaded"):
         # a new video: its poses arrive from the host and F is rebuilt (tiny 4x4 algebra) into the static buffer
         rel = camera.relative_c2w(cam_host["w2c"], torch.zeros(cam_host["w2c"].shape[0], dtype=torch.long))
         static["cam"]["epipolar_F"].copy_(camera.fundamental_matrices(cam_host["K"], rel), non_blocking=True)
@@ -300,6 +306,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--serial-passes", action="store_true", help="do not overlap the cond / uncond UNet passes inside the CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="camcontext", choices=["camcontext", "cami2v", "cameractrl", "motionctrl"],
+                    help="camera-conditioning blocks (BASELINE.json configs[4]: the R/baseline/* models through the same kernels)")
     ap.add_argument("--cfg-split", action="store_true",
                     help="latency mode: ranks (2k, 2k+1) share the videos of pair k, one runs the cond pass, the other the uncond pass")
     args = ap.parse_args()
@@ -331,7 +339,8 @@ def main():
         from camc2v_b200.parallel import make_cfg_pairs
         pair = make_cfg_pairs(rank, world)
     units = world // 2 if pair is not None else world          # independent video streams of the job
-    model, sampler, host, cam_host, _ = build_workload(cfg, B, device, seed_offset=(rank // 2 if pair is not None else rank))
+    model, sampler, host, cam_host, _ = build_workload(cfg, B, device, seed_offset=(rank // 2 if pair is not None else rank),
+                                                       variant=args.variant)
     sampler.cfg_pair = pair
     for k in ("x", "c_concat", "ctx_cond", "ctx_uncond"):
         host[k] = pin(host[k])
@@ -430,7 +439,8 @@ def main():
         dist.all_gather(gathered, x)
 
     if rank == 0:
-        step_flops = cfg_step_flops(cfg, B, 32)
+        step_flops = cfg_step_flops(cfg, B, 32, n_ctx_frames=2 if args.variant == "camcontext" else 0,
+                                    camera=args.variant in ("camcontext", "cami2v"))
         sustained = peaks[0].get("bf16_tflops_sustained", peaks[0]["bf16_tflops"])
         per_gpu_tflops = step_flops * (value / world) / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -443,6 +453,10 @@ def main():
                 "step_roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": sustained, "unit": "TFLOP/s",
                                   "frac": per_gpu_tflops / sustained, "flops_per_step": step_flops,
                                   "peak_source": f"{peaks[1]} sustained bf16 (whole step)"}}
+        if args.variant != "camcontext":
+            line["config"]["variant"] = args.variant
+            line["config"]["context_tokens"] = {"cond": 333, "uncond": 333}
+            line["config"]["workload"] = line["config"]["workload"].replace("CamContextI2V", f"{args.variant} baseline (BASELINE.json configs[4])")
         if pair is not None:
             line["config"]["parallelism"] = (f"cfg-split: {units} rank pairs, cond pass on even / uncond pass on odd ranks, one 2-rank "
                                              "NCCL all_gather of the noise predictions per step (latency mode)")

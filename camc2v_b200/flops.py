@@ -107,8 +107,11 @@ def unet_pass_flops(cfg: UNetConfig, B: int, hw: int, ctx_len: int, per_frame_ct
     return out
 
 
-def cfg_step_flops(cfg: UNetConfig, B: int, hw: int, n_ctx_frames: int = 2) -> float:
-    """One classifier-free-guidance DDIM step = cond pass (77 + 256*(1+n) tokens, broadcast) + uncond pass (77 + 256, per frame)."""
-    cond = unet_pass_flops(cfg, B, hw, cfg.text_context_len + 256 * (1 + n_ctx_frames), per_frame_ctx=False)["total"]
-    unc = unet_pass_flops(cfg, B, hw, cfg.text_context_len + 256, per_frame_ctx=True)["total"]
+def cfg_step_flops(cfg: UNetConfig, B: int, hw: int, n_ctx_frames: int = 2, camera: bool = True) -> float:
+    """One classifier-free-guidance DDIM step = cond pass (77 + 256*(1+n) tokens, broadcast; with n = 0 the per-frame rule of
+    modified_forwards.py:37-44 applies) + uncond pass (77 + 256, per frame).  camera=False drops the epipolar attention
+    (CameraCtrl / MotionCtrl baselines; their small cc_projection linears are not counted)."""
+    cond = unet_pass_flops(cfg, B, hw, cfg.text_context_len + 256 * (1 + n_ctx_frames), per_frame_ctx=(n_ctx_frames == 0),
+                           camera=camera)["total"]
+    unc = unet_pass_flops(cfg, B, hw, cfg.text_context_len + 256, per_frame_ctx=True, camera=camera)["total"]
     return cond + unc
