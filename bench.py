@@ -261,10 +261,12 @@ def time_dominant_kernel(device, peaks):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
     tmap = ops.epipolar_tile_map(Fm, T, H, W, d)       # built once per sample, as in the model path
+    from camc2v_b200 import modules as _m
+    bmask = ops.epipolar_bitmask(Fm, T, H, W, d) if _m.USE_EPI_BITMASK else None     # packed mask, also once per sample
 
     def launch():
         return ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm,
-                             epi_grid=(T, H, W), epi_d=d, epi_tile_map=tmap)
+                             epi_grid=(T, H, W), epi_d=d, epi_tile_map=tmap, epi_bitmask=bmask)
 
     for _ in range(3):
         launch()

@@ -35,7 +35,7 @@ class AttnDesc(C.Structure):
         ("kv_div", C.c_int), ("out_scale", C.c_float), ("accumulate", C.c_int),
         ("k2", C.c_void_p), ("v2", C.c_void_p), ("lk2", C.c_int), ("ldk2", C.c_int), ("ldv2", C.c_int),
         ("epi_F", C.c_void_p), ("epi_T", C.c_int), ("epi_H", C.c_int), ("epi_W", C.c_int), ("epi_d", C.c_int),
-        ("mask", C.c_void_p), ("mask_bstride", C.c_int64), ("epi_tile_map", C.c_void_p),
+        ("mask", C.c_void_p), ("mask_bstride", C.c_int64), ("epi_tile_map", C.c_void_p), ("epi_bitmask", C.c_void_p),
     ]
 
 
@@ -58,6 +58,8 @@ PROTOTYPES = {
     "c2v_epipolar_mask": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_epipolar_tile_map": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_epipolar_tile_map_words": (_i, [_i, _i, _i]),
+    "c2v_epipolar_bitmask": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "c2v_epipolar_bitmask_words": (_i64, [_i, _i, _i]),
     "c2v_plucker": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_to_channels_last": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_from_channels_last": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -284,6 +284,7 @@ int c2v_attention(const c2v_attn_desc* d, void* stream) {
         a.tile_map = d->epi_tile_map;
         a.tile_map_words = c2v_epipolar_tile_map_words(d->epi_T, d->epi_H, d->epi_W);
     }
+    if (d->epi_bitmask && d->epi_F && d->lq % 128 == 0) a.bitmask = d->epi_bitmask;
     return attn_tc_launch(a, (d->lq + 127) / 128, d->heads, d->bq, (cudaStream_t)stream);
 }
 
@@ -299,6 +300,13 @@ int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, 
 
 // bitmap words of one query-tile row (64-key tiles) + 1 word holding the longest-first issue order
 int c2v_epipolar_tile_map_words(int T, int H, int W) { return ((T * H * W + 63) / 64 + 31) / 32 + 1; }
+
+int64_t c2v_epipolar_bitmask_words(int T, int H, int W) { return (int64_t)T * H * W * (int64_t)(T * H * W / 32); }
+
+int c2v_epipolar_bitmask(const float* F, uint32_t* out, int B, int T, int H, int W, int d, void* stream) {
+    if (!F || !out || B <= 0) return ERR_BAD_ARG;
+    return epi_bitmask_launch(F, out, B, T, H, W, d, (cudaStream_t)stream);
+}
 
 int c2v_epipolar_tile_map(const float* F, uint32_t* map, int B, int T, int H, int W, int d, void* stream) {
     if (!F || !map || B <= 0 || B > 65535) return ERR_BAD_ARG;

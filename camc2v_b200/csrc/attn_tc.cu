@@ -270,6 +270,12 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
 
         for (int j = 0; j < n_act; ++j) {
             const int jt = tile_list[j];              // key tile index (j counts visited tiles: barrier parities)
+            uint32_t bw[AT_BN / 32] = {};             // packed mask words of this row for the tile's 32-key chunks
+            if (FAST && p.bitmask && jt < n_main) {   // issued before the wait for S: the load latency hides behind QK^T
+                const uint32_t* mrow_w = p.bitmask + (((size_t)b * gridDim.x + q_tile) * (size_t)(p.lk >> 5) + (size_t)jt * (AT_BN / 32)) * AT_BM + r;
+#pragma unroll
+                for (int c = 0; c < AT_BN / 32; ++c) bw[c] = __ldg(mrow_w + (size_t)c * AT_BM);
+            }
             mbar_wait(&s_full[j % AT_S_BUFS], (j / AT_S_BUFS) & 1);
             tc_fence_after();
             const uint32_t t_s = t_s0 + (uint32_t)(j % AT_S_BUFS) * AT_BN;
@@ -281,7 +287,23 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
             const int tile_key0 = main_seg ? jt * AT_BN : 0;
             // ---- pass 1: row max; masked / out-of-range scores are replaced by -inf IN TMEM (tcgen05.st), so that pass 2 is
             //      the same predicate-free exp2 loop for every flavour of attention (exp2(-inf) = 0) ----
-            if (FAST && epi && main_seg) {
+            if (FAST && epi && main_seg && p.bitmask) {
+                // Packed mask (c2v_epipolar_bitmask, built once per sample with the same arithmetic): one bit test per element
+#pragma unroll
+                for (int c = 0; c < AT_BN / 32; ++c) {
+                    if (__any_sync(0xffffffffu, bw[c] != 0u)) {
+                        uint32_t v[32];
+                        tmem_ld32(t_s + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = (bw[c] >> i) & 1u ? v[i] : NEG_INF_BITS;
+                        anyc |= 1u << c;
+                        wrote = true;
+                        tmem_st32(t_s + c * 32, v);
+                        mx = fmaxf(mx, max32(v));
+                    }
+                }
+            } else if (FAST && epi && main_seg) {
                 // Square power-of-two key grid: a 32-key chunk is RPC whole image rows of one frame, pixel x of column i
                 // is a compile-time constant and the reference's mask predicate costs FMUL+FFMA+FADD+FSETP per element.
                 constexpr int W = 1 << (FAST ? LOGW : 5);
@@ -499,6 +521,56 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed epipolar mask: out[b][q_tile][k_chunk][r] bit i = mask[b][128 q_tile + r][32 k_chunk + i], evaluated with exactly the
+// arithmetic of the in-kernel predicate above (and hence of the reference, camcontexti2v.py:229-239).  One CTA = 128 queries x
+// one key frame: the normalised line is computed once per (query, frame), then 32 predicates per word.
+// ------------------------------------------------------------------------------------------------
+template <int LOGW, int D>
+__global__ void __launch_bounds__(128) epi_bitmask_kernel(const float* __restrict__ Fm, unsigned int* __restrict__ out, int T, float thr) {
+    constexpr int W = 1 << LOGW, HW = W * W, RPC = 32 / W, CPF = HW / 32;      // chunks per frame
+    constexpr float DF = (float)D, OFFC = (float)D * 0.5f - 0.5f;
+    const int t2 = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
+    const int r = threadIdx.x;
+    const int qi = qt * AT_BM + r;
+    const int t1 = qi >> (2 * LOGW), pix = qi & (HW - 1);
+    const float xi = (float)(pix & (W - 1)) * DF + OFFC, yi = (float)(pix >> LOGW) * DF + OFFC;
+    const EpiLine line = epi_line(Fm + (((size_t)b * T + t1) * T + t2) * 9, xi, yi);
+    float l0x[W];
+#pragma unroll
+    for (int x = 0; x < W; ++x) l0x[x] = __fmul_rn(line.l0, (float)x * DF + OFFC);
+    const size_t n_chunks = (size_t)T * CPF;
+    unsigned int* o = out + (((size_t)b * gridDim.y + qt) * n_chunks + (size_t)t2 * CPF) * AT_BM + r;
+    for (int c = 0; c < CPF; ++c) {
+        unsigned int word = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float yr = (float)(c * RPC + (i >> LOGW)) * DF + OFFC;
+            const float wv = __fadd_rn(__fmaf_rn(line.l1, yr, l0x[i & (W - 1)]), line.l2);
+            word |= (fabsf(wv) < thr ? 1u : 0u) << i;
+        }
+        o[(size_t)c * AT_BM] = word;
+    }
+}
+
+int epi_bitmask_launch(const float* F, unsigned int* out, int B, int T, int H, int W, int d, cudaStream_t st) {
+    if (H != W) return ERR_UNSUPPORTED;
+    const int L = T * H * W;
+    if (L % AT_BM != 0 || B > 65535) return ERR_UNSUPPORTED;
+    const float thr = (float)((double)d * sqrt(2.0) / 2.0);
+    dim3 grid(T, L / AT_BM, B);
+#define C2V_BM(LW, DD) epi_bitmask_kernel<LW, DD><<<grid, 128, 0, st>>>(F, out, T, thr)
+    if (W == 32 && d == 8) C2V_BM(5, 8);
+    else if (W == 16 && d == 16) C2V_BM(4, 16);
+    else if (W == 8 && d == 32) C2V_BM(3, 32);
+    else if (W == 16 && d == 8) C2V_BM(4, 8);
+    else if (W == 8 && d == 16) C2V_BM(3, 16);
+    else return ERR_UNSUPPORTED;
+#undef C2V_BM
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Epipolar tile map: bit (q_tile, k_tile) = "some query of the 128-query tile may see some key of the 64-key tile".
 // Same conservative per-image-row interval test (and the same rounding margin) as the in-tile row skip of attn_tc_kernel,
 // so a cleared bit implies every chunk of that tile would have been skipped anyway: results are bit-identical with and
@@ -610,7 +682,8 @@ int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, c
         if (w == 8 && d == 16) return launch_attn<3, 16>(a, q_tiles, heads, batch, st);
     }
     AttnKernelArgs g = a;
-    g.tile_map = nullptr;                     // the tile map is defined for the power-of-two grids only
+    g.tile_map = nullptr;                     // the tile map / packed mask are defined for the power-of-two grids only
+    g.bitmask = nullptr;
     return launch_attn<0, 1>(g, q_tiles, heads, batch, st);
 }
 

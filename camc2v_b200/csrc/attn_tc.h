@@ -25,10 +25,13 @@ struct AttnKernelArgs {
     // optional epipolar tile map: bit j of row (b, q_tile) = key tile j may contain an unmasked pair
     const unsigned int* tile_map;
     int tile_map_words;
+    // optional packed mask [B][q_tile][k_chunk][128] (bit i of a word = key 32*k_chunk + i)
+    const unsigned int* bitmask;
     float epi_thr, epi_off;      // float32(d*sqrt(2)/2), d/2 - 0.5
 };
 
 int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st);
+int epi_bitmask_launch(const float* F, unsigned int* out, int B, int T, int H, int W, int d, cudaStream_t st);
 int epi_tile_map_launch(const float* F, unsigned int* map, int B, int T, int H, int W, int d, cudaStream_t st);
 
 }  // namespace c2v

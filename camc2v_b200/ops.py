@@ -153,7 +153,7 @@ def layernorm(x: torch.Tensor, gamma, beta, add: Optional[torch.Tensor] = None, 
 
 # ------------------------------------------------------------------------------------------------ attention
 def attention(q, k, v, bq: int, lq: int, lk: int, heads: int, kv_div: int = 1, out=None, out_scale: float = 1.0, accumulate: bool = False,
-              k2=None, v2=None, epi_F=None, epi_grid=None, epi_d: int = 0, mask=None, epi_tile_map=None):
+              k2=None, v2=None, epi_F=None, epi_grid=None, epi_d: int = 0, mask=None, epi_tile_map=None, epi_bitmask=None):
     """q [bq*lq, >=heads*64] bf16 (row-strided view allowed), k/v [bk*lk, ...]; returns bf16 [bq*lq, heads*64]."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, BF16, "attention." + n)
@@ -176,6 +176,8 @@ def attention(q, k, v, bq: int, lq: int, lk: int, heads: int, kv_div: int = 1, o
         d.epi_F, d.epi_T, d.epi_H, d.epi_W, d.epi_d = _p(epi_F), T, H, W, epi_d
         if epi_tile_map is not None:
             d.epi_tile_map = _p(epi_tile_map)
+        if epi_bitmask is not None:
+            d.epi_bitmask = _p(epi_bitmask)
     if mask is not None:
         if mask.dtype not in (torch.bool, torch.uint8) or not mask.is_contiguous():
             raise _lib.C2VError("attention.mask must be contiguous bool/uint8 [bq, lq, lk]")
@@ -202,6 +204,21 @@ def epipolar_mask(F: torch.Tensor, H: int, W: int, d: int) -> torch.Tensor:
     out = torch.empty((B, L, L), device=F.device, dtype=torch.uint8)
     _lib.call("c2v_epipolar_mask", _p(F), _p(out), B, T, H, W, d, _stream())
     return out.view(torch.bool)
+
+
+def epipolar_bitmask(F: torch.Tensor, T: int, H: int, W: int, d: int, out=None):
+    """The epipolar mask packed to bits for attention(..., epi_F=F, epi_bitmask=...): int32 [B, q_tiles, k_chunks, 128]
+    (bit i of word [b, qt, c, r] = mask[b, 128 qt + r, 32 c + i]); None when the grid has no fast path."""
+    _chk(F, F32, "epipolar_bitmask.F")
+    L = T * H * W
+    if H != W or (W, d) not in ((32, 8), (16, 16), (8, 32), (16, 8), (8, 16)) or L % 128:
+        return None
+    B = F.shape[0]
+    if out is None:
+        out = torch.empty((B, L // 128, L // 32, 128), device=F.device, dtype=torch.int32)
+    assert out.numel() == B * _lib.load().c2v_epipolar_bitmask_words(T, H, W)
+    _lib.call("c2v_epipolar_bitmask", _p(F.contiguous()), _p(out), B, T, H, W, d, _stream())
+    return out
 
 
 def epipolar_tile_map(F: torch.Tensor, T: int, H: int, W: int, d: int, out=None):

@@ -126,6 +126,9 @@ typedef struct c2v_attn_desc {
     const uint8_t* mask; int64_t mask_bstride;
     const uint32_t* epi_tile_map;  /* optional (with epi_F): output of c2v_epipolar_tile_map for the same F and grid; key tiles that
                                       cannot hold an unmasked pair are skipped entirely (results are bit-identical without it) */
+    const uint32_t* epi_bitmask;   /* optional (with epi_F): output of c2v_epipolar_bitmask for the same F and grid: the mask packed
+                                      to 1 bit per (query, key) pair, so the kernel tests a bit instead of re-evaluating the
+                                      predicate in every layer / pass / step (results are bit-identical without it) */
 } c2v_attn_desc;
 int c2v_attention(const c2v_attn_desc* d, void* stream);
 
@@ -145,6 +148,11 @@ int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, 
  * Returns 4 (unsupported) for other grids: callers then simply pass no map. */
 int c2v_epipolar_tile_map(const float* F, uint32_t* map, int B, int T, int H, int W, int d, void* stream);
 int c2v_epipolar_tile_map_words(int T, int H, int W);
+/* The mask of camcontexti2v.py:202-271 packed to bits in the layout c2v_attention reads with coalesced 128-byte loads:
+ * out[b][q_tile][k_chunk][r] (uint32), bit i = mask[b][128*q_tile + r][32*k_chunk + i]; T*H*W * T*H*W / 8 bytes per batch
+ * element (32 MB at 32x32x16, against 268 MB for the reference's bool mask).  Same supported grids as the tile map. */
+int c2v_epipolar_bitmask(const float* F, uint32_t* out, int B, int T, int H, int W, int d, void* stream);
+int64_t c2v_epipolar_bitmask_words(int T, int H, int W);      /* uint32 words per batch element */
 /* Pluecker / ray embedding (R/model/base.py:112-174): K fp32 [B,T,3,3], c2w fp32 [B,T,4,4] -> fp32 [B,6,T,H,W]. */
 int c2v_plucker(const float* K, const float* c2w, float* out, int B, int T, int H, int W, int plucker, void* stream);
 

@@ -262,6 +262,19 @@ def test_attention_epipolar(T, H, W, d, heads, kind):
         occ = mpad.view(nt, 128, nk, 64).any(dim=3).any(dim=1)
         assert bool((bits | ~occ).all()), "tile map cleared a tile that contains an attended pair"
         print(f"tile map {kind} {H}x{W}: {bits.float().mean():.3f} of tiles visited, {occ.float().mean():.3f} truly occupied")
+        # packed mask: every bit equals the reference's mask, and attention driven by it is bit-identical to the in-kernel predicate
+        bm = ops.epipolar_bitmask(Fm.to(DEV).contiguous(), T, H, W, d)                  # [1, nt, L/32, 128] int32
+        assert bm is not None and bm.shape == (1, nt, L // 32, 128)
+        w = bm[0].cpu().numpy().astype(np.uint32)                                        # [qt, chunk, r]
+        unpacked = ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)   # [qt, chunk, r, i]
+        unpacked = np.transpose(unpacked, (0, 2, 1, 3)).reshape(nt * 128, L)[:L]
+        assert np.array_equal(unpacked, mask[0].cpu().numpy()), "packed epipolar mask differs from the reference mask"
+        out_b = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm.to(DEV).contiguous(), epi_grid=(T, H, W),
+                              epi_d=d, epi_tile_map=tmap, epi_bitmask=bm)
+        assert torch.equal(out, out_b)
+        out_b2 = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm.to(DEV).contiguous(), epi_grid=(T, H, W),
+                               epi_d=d, epi_bitmask=bm)
+        assert torch.equal(out, out_b2)
 
 
 @pytest.mark.parametrize("B,T,HW,heads", [(1, 16, 1024, 5), (2, 16, 64, 20), (1, 16, 256, 8), (1, 8, 16, 4)])

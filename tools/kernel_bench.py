@@ -150,8 +150,9 @@ def single(which):
         torch.manual_seed(123)
         Fm = camera.fundamental_matrices(K, camera.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))).to(DEV).contiguous()
         tmap = ops.epipolar_tile_map(Fm, T, H, H, d)
+        bmask = ops.epipolar_bitmask(Fm, T, H, H, d)
         fn = lambda: ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], 1, L, L, h, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm,
-                                   epi_grid=(T, H, H), epi_d=d, epi_tile_map=tmap)
+                                   epi_grid=(T, H, H), epi_d=d, epi_tile_map=tmap, epi_bitmask=bmask)
     elif which == "geglu0":
         a, w, b = rb(16384, 320), rb(2560, 320), rb(2560, dtype=torch.float32)
         wi, bi = ops.geglu_interleave(w, b)
