@@ -25,6 +25,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if "--operands" in sys.argv[:-1]:       # the library flavour is chosen when camc2v_b200._lib is first imported
+    os.environ["CAMC2V_B200_OPERANDS"] = sys.argv[sys.argv.index("--operands") + 1]
 
 from camc2v_b200 import synth  # noqa: E402
 from camc2v_b200.config import UNetConfig  # noqa: E402
@@ -253,8 +255,8 @@ def time_dominant_kernel(device, peaks):
     T, H, W, heads, d = 16, 32, 32, 5, 8
     L, C = T * H * W, heads * 64
     g = torch.Generator(device="cpu").manual_seed(0)
-    qkv = torch.randn(L, 3 * C, generator=g).to(device).to(torch.bfloat16)
-    reg = torch.randn(4, 2 * C, generator=g).to(device).to(torch.bfloat16)
+    qkv = torch.randn(L, 3 * C, generator=g).to(device).to(ops.BF16)
+    reg = torch.randn(4, 2 * C, generator=g).to(device).to(ops.BF16)
     K, w2c = synth.synth_camera("pan_yaw", T=T)
     torch.manual_seed(123)
     Fm = camera.fundamental_matrices(K, camera.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))).to(device).contiguous()
@@ -308,6 +310,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--serial-passes", action="store_true", help="do not overlap the cond / uncond UNet passes inside the CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--operands", default=os.environ.get("CAMC2V_B200_OPERANDS", "fp16"), choices=["bf16", "fp16"],
+                    help="16-bit tensor-core operand type of the library build (fp32 accumulate either way, same speed): fp16 is the "
+                         "reference's own 16-mixed precision and the default; bf16 is the other shipped build")
     ap.add_argument("--variant", default="camcontext", choices=["camcontext", "cami2v", "cameractrl", "motionctrl"],
                     help="camera-conditioning blocks (BASELINE.json configs[4]: the R/baseline/* models through the same kernels)")
     ap.add_argument("--cfg-split", action="store_true",
@@ -446,7 +451,7 @@ def main():
         sustained = peaks[0].get("bf16_tflops_sustained", peaks[0]["bf16_tflops"])
         per_gpu_tflops = step_flops * (value / world) / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": _lib.OPERANDS,
                 "data": "synthetic", "config": workload_config(B, world),
                 "videos_per_s": value / steps_per_video,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},

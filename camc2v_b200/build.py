@@ -15,6 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcamc2v_b200.so")
+OUT_FP16 = os.path.join(HERE, "libcamc2v_b200_fp16.so")        # same kernels with IEEE-half operands (-DC2V_OPERAND_FP16)
 OBJ = os.path.join(HERE, "csrc", "_obj")
 SOURCES = ["api.cu", "gemm_tc.cu", "attn_tc.cu", "attn_t16.cu", "norm.cu", "elementwise.cu", "epipolar.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -29,7 +30,14 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, fp16: bool = False) -> str:
+    out = OUT_FP16 if fp16 else OUT
+    obj_dir = os.path.join(HERE, "csrc", "_obj_fp16" if fp16 else "_obj")
+    extra = ["-DC2V_OPERAND_FP16"] if fp16 else []
+    return _build(out, obj_dir, extra, force, verbose)
+
+
+def _build(OUT: str, OBJ: str, extra, force: bool, verbose: bool) -> str:
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "camc2v_b200.h"))
@@ -38,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJ, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + headers):
-            jobs.append([NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+            jobs.append([NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,4 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--fp16" in sys.argv or "--all" in sys.argv:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, fp16=True))
+    if "--fp16" not in sys.argv:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

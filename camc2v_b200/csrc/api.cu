@@ -15,6 +15,12 @@ extern "C" {
 
 int c2v_abi_version(void) { return 1; }
 
+#ifdef C2V_OPERAND_FP16
+int c2v_operand_dtype(void) { return 1; }
+#else
+int c2v_operand_dtype(void) { return 0; }
+#endif
+
 const char* c2v_status_string(int s) {
     switch (s) {
         case OK: return "ok";
@@ -177,7 +183,7 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
             const uint64_t odims[3] = {(uint64_t)d->N, (uint64_t)d->M, (uint64_t)a.splits};
             const uint64_t ostr[2] = {ld * esz, (uint64_t)d->M * ld * esz};
             const uint32_t obox[3] = {32, (uint32_t)a.tile_rows, 1};
-            if (!make_tmap(&a.tmO, obase, 3, odims, ostr, obox, o_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+            if (!make_tmap(&a.tmO, obase, 3, odims, ostr, obox, o_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (C2V_OPERAND_IS_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16),
                            o_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
                 return ERR_TMA_ENCODE;
             if (d->residual && !part) {

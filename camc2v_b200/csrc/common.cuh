@@ -3,9 +3,28 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+
+// ------------------------------------------------------------------------------------------------
+// 16-bit operand type of every tensor-core GEMM / attention operand and of every bf16 activation buffer.
+// Default: bfloat16.  -DC2V_OPERAND_FP16 builds the same kernels with IEEE half operands (what the reference's own
+// "16-mixed" autocast uses): 11 significand bits instead of 8, i.e. ~8x smaller operand rounding error at identical
+// speed; accumulation, statistics, softmax and the residual stream stay fp32 either way.  The kernels are written against
+// the bf16 names; this block re-points those names at the half type, so one flag flips the whole library consistently.
+// ------------------------------------------------------------------------------------------------
+#ifdef C2V_OPERAND_FP16
+#define __nv_bfloat16 __half
+#define __nv_bfloat162 __half2
+#define __bfloat1622float2 __half22float2
+#define __float2bfloat16 __float2half
+#define __floats2bfloat162_rn __floats2half2_rn
+#define C2V_OPERAND_IS_FP16 1
+#else
+#define C2V_OPERAND_IS_FP16 0
+#endif
 
 namespace c2v {
 
@@ -154,7 +173,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // (cute::UMMA::InstrDescriptor): c_format[4,6)=1 (F32), a_format[7,10)=1, b_format[10,13)=1 (BF16),
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), n_dim[17,23) = N>>3, m_dim[24,29) = M>>4.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+    // c_format = f32 (bit 4); a_format / b_format (bits 7 / 10): 1 = bf16, 0 = f16
+    return (1u << 4) | ((C2V_OPERAND_IS_FP16 ? 0u : 1u) << 7) | ((C2V_OPERAND_IS_FP16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

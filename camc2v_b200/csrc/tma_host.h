@@ -29,7 +29,11 @@ inline bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t
 
 inline bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box) {
+#ifdef C2V_OPERAND_FP16
+    return make_tmap(m, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_128B);
+#else
     return make_tmap(m, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B);
+#endif
 }
 
 inline bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,

@@ -28,10 +28,10 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .config import Layer, UNetConfig, build_topology
 
-BF16 = torch.bfloat16
+BF16 = _lib.operand_torch_dtype()      # the library's 16-bit operand type: bfloat16 (default build) or float16
 F32 = torch.float32
 
 

@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import A_CONV2D, A_CONVT, A_PLAIN, EPI_GEGLU, EPI_LINEAR, AttnDesc, GemmDesc
 
-BF16 = torch.bfloat16
+BF16 = _lib.operand_torch_dtype()      # the library's 16-bit operand type: bfloat16 (default build) or float16
 F32 = torch.float32
 
 

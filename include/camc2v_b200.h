@@ -28,6 +28,10 @@ extern "C" {
 
 /* Library / ABI version; also proves the shared object is the CUDA build (smoke tests check it). */
 int c2v_abi_version(void);
+/* 16-bit operand type this build of the library uses for every `bf16` buffer of this header: 0 = bfloat16 (default build),
+ * 1 = IEEE half (the -DC2V_OPERAND_FP16 build, libcamc2v_b200_fp16.so): same kernels, same speed, ~8x smaller operand
+ * rounding error; accumulation / statistics / softmax / residual stream are fp32 in both. */
+int c2v_operand_dtype(void);
 /* Human-readable string for a status code returned by any entry point (host pointer, static storage). */
 const char* c2v_status_string(int status);
 

@@ -25,7 +25,9 @@ def _declared_symbols():
 def test_library_builds_and_exports_every_declared_symbol():
     from camc2v_b200 import _lib, build
     path = build.build()
-    assert os.path.exists(path)
+    path16 = build.build(fp16=True)               # both operand flavours ship: bf16 and (default) IEEE half
+    assert os.path.exists(path) and os.path.exists(path16)
+    assert ctypes.CDLL(path).c2v_operand_dtype() == 0 and ctypes.CDLL(path16).c2v_operand_dtype() == 1
     lib = ctypes.CDLL(path)
     declared = _declared_symbols()
     assert len(declared) >= 20

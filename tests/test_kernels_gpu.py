@@ -26,6 +26,12 @@ def rnd(*shape, seed=0, std=1.0, dtype=torch.float32):
     return (torch.randn(*shape, generator=g) * std).to(DEV).to(dtype)
 
 
+def _dt():
+    """16-bit operand dtype of the library under test (bfloat16, or float16 with CAMC2V_B200_OPERANDS=fp16)."""
+    from camc2v_b200 import ops
+    return ops.BF16
+
+
 def close(out, ref, tol, what=""):
     out, ref = out.float(), ref.float()
     assert torch.isfinite(out).all(), f"{what}: non-finite output"
@@ -39,14 +45,14 @@ def close(out, ref, tol, what=""):
                                    (128, 4, 320), (300, 2560, 1280), (256, 1280, 5120)])
 def test_linear(M, N, K):
     ops = _ops()
-    a = rnd(M, K, seed=1, dtype=torch.bfloat16)
-    w = rnd(N, K, seed=2, std=K ** -0.5, dtype=torch.bfloat16)
+    a = rnd(M, K, seed=1, dtype=_dt())
+    w = rnd(N, K, seed=2, std=K ** -0.5, dtype=_dt())
     bias = rnd(N, seed=3)
     res = rnd(M, N, seed=4)
     ref = a.float() @ w.float().t() + bias + res
     out = ops.linear(a, w, bias=bias, residual=res)
     close(out, ref, 2e-3, "linear fp32")
-    out16 = ops.linear(a, w, bias=bias, residual=res, out_dtype=torch.bfloat16)
+    out16 = ops.linear(a, w, bias=bias, residual=res, out_dtype=_dt())
     close(out16, ref, 1e-2, "linear bf16")
     # in-place residual (out aliases residual), as used for the attention / FF residual adds
     res2 = res.clone()
@@ -61,10 +67,10 @@ def test_splitk_cluster_reduce_matches_workspace_path(M, N, K, bf16):
     run-to-run identical."""
     ops = _ops()
     assert ops._lib.load().c2v_gemm_splitk(M, N, K, 1, 0) > 1
-    a = rnd(M, K, seed=1, dtype=torch.bfloat16)
-    w = rnd(N, K, seed=2, std=K ** -0.5, dtype=torch.bfloat16)
+    a = rnd(M, K, seed=1, dtype=_dt())
+    w = rnd(N, K, seed=2, std=K ** -0.5, dtype=_dt())
     bias, res, rb = rnd(N, seed=3), rnd(M, N, seed=4), rnd((M + 127) // 128, N, seed=5)
-    odt = torch.bfloat16 if bf16 else torch.float32
+    odt = _dt() if bf16 else torch.float32
     ref = a.float() @ w.float().t() + bias + res + rb.repeat_interleave(128, dim=0)[:M]
     outs = []
     for legacy in (False, True, False):
@@ -81,9 +87,9 @@ def test_splitk_cluster_reduce_matches_workspace_path(M, N, K, bf16):
 def test_linear_strided_a_and_rowbias():
     ops = _ops()
     M, K, N = 512, 320, 640
-    big = rnd(M, 3 * K, seed=5, dtype=torch.bfloat16)
+    big = rnd(M, 3 * K, seed=5, dtype=_dt())
     a = big[:, K:2 * K]
-    w = rnd(N, K, seed=6, std=K ** -0.5, dtype=torch.bfloat16)
+    w = rnd(N, K, seed=6, std=K ** -0.5, dtype=_dt())
     rb = rnd(4, N, seed=7)
     ref = a.float() @ w.float().t() + rb.repeat_interleave(128, dim=0)
     out = ops.linear(a, w, rowbias=rb, rows_per_group=128)
@@ -94,8 +100,8 @@ def test_linear_strided_a_and_rowbias():
 def test_geglu(C):
     ops = _ops()
     M = 384
-    a = rnd(M, C, seed=1, dtype=torch.bfloat16)
-    w = rnd(8 * C, C, seed=2, std=C ** -0.5, dtype=torch.bfloat16)
+    a = rnd(M, C, seed=1, dtype=_dt())
+    w = rnd(8 * C, C, seed=2, std=C ** -0.5, dtype=_dt())
     b = rnd(8 * C, seed=3, std=0.1)
     y = a.float() @ w.float().t() + b
     x, gate = y.chunk(2, dim=-1)
@@ -113,7 +119,7 @@ def test_conv3x3(NB, H, W, Cin, Cout):
     x = rnd(NB, Cin, H, W, seed=1)
     w = rnd(Cout, Cin, 3, 3, seed=2, std=(9 * Cin) ** -0.5)
     b = rnd(Cout, seed=3)
-    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    xb, wb = x.to(_dt()), w.to(_dt())
     ref = torch.nn.functional.conv2d(xb.float(), wb.float(), b, padding=1)
     a = xb.permute(0, 2, 3, 1).reshape(NB * H * W, Cin).contiguous()
     wk = wb.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
@@ -130,7 +136,7 @@ def test_conv_t3(B, T, HW, C):
     x = rnd(B, C, T, HW, 1, seed=1)
     w = rnd(C, C, 3, 1, 1, seed=2, std=(3 * C) ** -0.5)
     b = rnd(C, seed=3)
-    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    xb, wb = x.to(_dt()), w.to(_dt())
     ref = torch.nn.functional.conv3d(xb.float(), wb.float(), b, padding=(1, 0, 0))          # [B, C, T, HW, 1]
     a = xb.squeeze(-1).permute(0, 2, 3, 1).reshape(B * T * HW, C).contiguous()
     wk = wb.reshape(C, C, 3).permute(0, 2, 1).reshape(C, 3 * C).contiguous()
@@ -151,7 +157,7 @@ def test_skinny_linear_and_timestep_embedding():
     ref = torch.cat([torch.cos(args), torch.sin(args)], dim=-1).to(DEV)
     assert (emb - ref).abs().max().item() < 2e-4      # fp32 sin/cos of arguments up to 999 rad
     x = rnd(4, 320, seed=1)
-    w = rnd(1280, 320, seed=2, std=320 ** -0.5, dtype=torch.bfloat16)
+    w = rnd(1280, 320, seed=2, std=320 ** -0.5, dtype=_dt())
     b = rnd(1280, seed=3)
     close(ops.skinny_linear(x, w, b, False), x @ w.float().t() + b, 1e-5, "skinny")
     close(ops.skinny_linear(x, w, b, True), torch.nn.functional.silu(x) @ w.float().t() + b, 1e-5, "skinny silu")
@@ -205,12 +211,12 @@ def test_attention_dense(bq, lq, lk, heads, kv_div):
     ops = _ops()
     C = heads * 64
     bk = bq // kv_div
-    qkv = rnd(bq * lq, 3 * C, seed=1, dtype=torch.bfloat16)
+    qkv = rnd(bq * lq, 3 * C, seed=1, dtype=_dt())
     q = qkv[:, :C]
     if lq == lk and kv_div == 1:
         k, v = qkv[:, C:2 * C], qkv[:, 2 * C:]
     else:
-        kv = rnd(bk * lk, 2 * C, seed=2, dtype=torch.bfloat16)
+        kv = rnd(bk * lk, 2 * C, seed=2, dtype=_dt())
         k, v = kv[:, :C], kv[:, C:]
     out = ops.attention(q, k, v, bq, lq, lk, heads, kv_div=kv_div)
     kk = k.reshape(bk, lk, C).repeat_interleave(kv_div, dim=0)
@@ -236,8 +242,8 @@ def test_attention_epipolar(T, H, W, d, heads, kind):
     Fm = camera_oracle.fundamental_matrices(K, rel)
     mask = oracle.epipolar_mask(Fm, H, W, d).to(DEV)              # [1, L, L]
     L, C, R = T * H * W, heads * 64, 4
-    qkv = rnd(L, 3 * C, seed=1, dtype=torch.bfloat16)
-    reg = rnd(R, 2 * C, seed=2, dtype=torch.bfloat16)
+    qkv = rnd(L, 3 * C, seed=1, dtype=_dt())
+    reg = rnd(R, 2 * C, seed=2, dtype=_dt())
     q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
     out = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm.to(DEV).contiguous(), epi_grid=(T, H, W), epi_d=d)
     kk = torch.cat([reg[:, :C], k], 0)[None]
@@ -281,7 +287,7 @@ def test_attention_epipolar(T, H, W, d, heads, kind):
 def test_attention_temporal(B, T, HW, heads):
     ops = _ops()
     C = heads * 64
-    qkv = rnd(B * T * HW, 3 * C, seed=1, dtype=torch.bfloat16)
+    qkv = rnd(B * T * HW, 3 * C, seed=1, dtype=_dt())
     out = ops.attention_temporal(qkv, B, T, HW, heads)
     x = qkv.view(B, T, HW, 3, C).permute(3, 0, 2, 1, 4).reshape(3, B * HW, T, C)
     ref = ref_attention(x[0], x[1], x[2], heads).view(B, HW, T, C).permute(0, 2, 1, 3).reshape(B * T * HW, C)
@@ -331,32 +337,32 @@ def test_layout_and_glue():
     ops = _ops()
     B, Cc, T, H, W = 2, 8, 16, 32, 32
     x = rnd(B, Cc, T, H, W, seed=1)
-    cl = ops.to_channels_last(x, B, Cc, T * H * W, Cpad=64, dtype=torch.bfloat16)
+    cl = ops.to_channels_last(x, B, Cc, T * H * W, Cpad=64, dtype=_dt())
     ref = torch.zeros(B * T * H * W, 64, device=DEV)
     ref[:, :Cc] = x.permute(0, 2, 3, 4, 1).reshape(-1, Cc)
-    assert torch.equal(cl.float(), ref.to(torch.bfloat16).float())
+    assert torch.equal(cl.float(), ref.to(_dt()).float())
     y = rnd(B * T * H * W, 4, seed=2)
     back = ops.from_channels_last(y, B, 4, T * H * W)
     assert torch.equal(back.view(B, 4, T, H, W), y.view(B, T, H, W, 4).permute(0, 4, 1, 2, 3))
     a, b = rnd(1000, 320, seed=3), rnd(1000, 640, seed=4)
     of, ob = ops.concat_channels(a, b, True, True)
-    assert torch.equal(of, torch.cat([a, b], 1)) and torch.equal(ob, torch.cat([a, b], 1).to(torch.bfloat16))
-    assert torch.equal(ops.cast_bf16(a), a.to(torch.bfloat16))
+    assert torch.equal(of, torch.cat([a, b], 1)) and torch.equal(ob, torch.cat([a, b], 1).to(_dt()))
+    assert torch.equal(ops.cast_bf16(a), a.to(_dt()))
     img = rnd(4 * 8 * 8, 64, seed=5)
     up = ops.upsample2x(img, 4, 8, 8)
     ref_up = torch.nn.functional.interpolate(img.view(4, 8, 8, 64).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
-    assert torch.equal(up.view(4, 16, 16, 64), ref_up.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert torch.equal(up.view(4, 16, 16, 64), ref_up.permute(0, 2, 3, 1).to(_dt()))
     col = ops.im2col_s2(img, 4, 8, 8)
     unf = torch.nn.functional.unfold(img.view(4, 8, 8, 64).permute(0, 3, 1, 2), 3, padding=1, stride=2)   # [4, 64*9, 16]
     ref_col = unf.view(4, 64, 9, 16).permute(0, 3, 2, 1).reshape(4 * 16, 9 * 64)
-    assert torch.equal(col, ref_col.to(torch.bfloat16))
+    assert torch.equal(col, ref_col.to(_dt()))
 
 
 def test_downsample_conv_via_im2col():
     ops = _ops()
     NB, H, W, C = 16, 16, 16, 128
-    x = rnd(NB, C, H, W, seed=1).to(torch.bfloat16).float()
-    w = rnd(C, C, 3, 3, seed=2, std=(9 * C) ** -0.5).to(torch.bfloat16)
+    x = rnd(NB, C, H, W, seed=1).to(_dt()).float()
+    w = rnd(C, C, 3, 3, seed=2, std=(9 * C) ** -0.5).to(_dt())
     b = rnd(C, seed=3)
     ref = torch.nn.functional.conv2d(x, w.float(), b, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, C)
     col = ops.im2col_s2(x.permute(0, 2, 3, 1).reshape(-1, C).contiguous(), NB, H, W)

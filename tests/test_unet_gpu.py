@@ -1,11 +1,15 @@
 """GPU parity tests of the module mirrors and of the full denoising step against (a) the golden outputs of the
 unmodified reference (tests/golden) and (b) the CPU oracle on the same seeded inputs.
 
-Stated tolerance (floating point, bf16 tensor-core operands with fp32 accumulation, fp32 residual stream / norm
-statistics / softmax): per UNet pass  rel-L2 <= 2e-2  and  max|err|/max|ref| <= 2e-2  against the reference's fp32
-result.  Calibration: the reference itself under naive bf16 autocast is 2.2e-2 / 3.3e-2 away from its own fp32
-result; this implementation measures ~1.3e-2 / ~1.2e-2.  Element-wise relative
-error is meaningless near zeros, so both metrics are norm-wise.  Mask decisions are bit-exact (test_kernels_gpu.py).
+Stated tolerance (floating point; 16-bit tensor-core operands with fp32 accumulation, fp32 residual stream / norm
+statistics / softmax), norm-wise against the reference's fp32 result, for a UNet pass, a CFG step and the 25-step loop:
+  * default build, IEEE-half operands (the reference's own 16-mixed precision):  rel-L2 <= 5e-3 and max|err|/max|ref| <= 5e-3
+    (measured on B200: 1.5e-3 / 1.3e-3 for the full-size pass, 1.2e-3 for the 25-step loop) - inside the north star's 1e-2;
+  * bf16-operand build (tests/test_bf16_build_gpu.py re-runs this file on it): <= 2e-2 (measured 1.3e-2 / 1.1e-2; bf16 weight
+    rounding alone costs 1.1e-2, oracle/refgen/rounding_study.py; the reference itself under bf16 autocast is 2.2e-2 / 3.3e-2
+    away from its own fp32 result).
+Element-wise relative error is meaningless near zeros, so both metrics are norm-wise.  Mask decisions are bit-exact
+(test_kernels_gpu.py).
 """
 import os
 
@@ -17,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda"
-TOL_L2, TOL_MAX = 2e-2, 2e-2
+TOL_L2 = TOL_MAX = float(os.environ.get("C2V_TEST_TOL", "5e-3"))      # tests/test_bf16_build_gpu.py re-runs this file at 2e-2 on the bf16 build
 
 
 def rel(a, b):
@@ -212,7 +216,7 @@ def test_baseline_variants_vs_oracle(variant):
     y = unet(xc.to(DEV), t.to(DEV), context=inp["ctx_uncond"].to(DEV), fs=inp["fs"].to(DEV), camera_condition=cam_d)
     # CameraCtrl feeds attn1 with n + cc_projection(n + p); with the (normally zero-initialised) cc_projection re-randomised at
     # unit scale the attention logits double, which amplifies bf16 operand rounding: 2.1e-2 measured, bound 2.5e-2 for this case.
-    tol = 2.5e-2 if variant == "cameractrl" else TOL_L2
+    tol = 1.25 * TOL_L2 if variant == "cameractrl" else TOL_L2
     l2, mx = rel(y, y_ref)
     assert l2 < tol and mx < tol, (variant, l2, mx)
     if variant != "none":      # and against the golden output of the reference's own baseline class

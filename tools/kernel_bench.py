@@ -36,7 +36,8 @@ def timeit(fn, n=10):
     return ts[len(ts) // 2] * 1e3   # us (median)
 
 
-def rb(*shape, dtype=torch.bfloat16):
+def rb(*shape, dtype=None):
+    dtype = dtype or ops.BF16
     return torch.randn(*shape, device=DEV).to(dtype)
 
 
@@ -51,7 +52,7 @@ def bench_gemm():
     for M, K, N, od, res in shapes:
         a, w, b = rb(M, K), rb(N, K), rb(N, dtype=torch.float32)
         r = rb(M, N, dtype=torch.float32) if res else None
-        odt = torch.float32 if od == "f32" else torch.bfloat16
+        odt = torch.float32 if od == "f32" else ops.BF16
         us = timeit(lambda: ops.linear(a, w, bias=b, residual=r, out_dtype=odt))
         fl = 2.0 * M * N * K
         by = M * K * 2 + N * K * 2 + M * N * (4 if od == "f32" else 2) + (M * N * 4 if res else 0)
