@@ -25,7 +25,7 @@ def operand_torch_dtype():
     return torch.float16 if OPERANDS == "fp16" else torch.bfloat16
 
 A_PLAIN, A_CONV2D, A_CONVT = 0, 1, 2
-EPI_LINEAR, EPI_GEGLU = 0, 1
+EPI_LINEAR, EPI_GEGLU, EPI_GELU = 0, 1, 2
 
 
 class GemmDesc(C.Structure):
@@ -70,6 +70,7 @@ PROTOTYPES = {
     "c2v_attention": (_i, [C.POINTER(AttnDesc), _vp]),
     "c2v_attention_temporal": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "c2v_epipolar_mask": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "c2v_epipolar_mask_rect": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "c2v_epipolar_tile_map": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_epipolar_tile_map_words": (_i, [_i, _i, _i]),
     "c2v_epipolar_bitmask": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -70,3 +70,18 @@ def camera_condition(K: torch.Tensor, w2c: torch.Tensor, cond_frame_index: torch
         out["sample_locs_dict"] = {int(8 * ds): ops.epipolar_mask(Fm, H // int(8 * ds), W // int(8 * ds), int(8 * ds))
                                    for ds in attention_resolution}
     return out
+
+
+def conditional_fundamental_matrices(K: torch.Tensor, w2c: torch.Tensor, w2c_cond: torch.Tensor, cond_frame_index: Optional[torch.Tensor]):
+    """F [B, T, C, 3, 3] between the T target frames and the C = 1 + n context frames (reference frame first) for the adaptor's
+    conditional epipolar mask (compute_conditional_epipolar_mask, R/model/camcontexti2v.py:493-521; get_pairwise_relative_pose,
+    R/model/base.py:200-217).  Tiny 4x4 algebra, done with torch on the host like the rest of this file; the mask itself is
+    ops.epipolar_mask(F, h, w, d)."""
+    c2w = w2c.float().inverse()
+    c2w_cond = w2c_cond.float().inverse()
+    if cond_frame_index is not None:
+        c2w_cond = torch.cat((c2w[torch.arange(len(cond_frame_index)), cond_frame_index].unsqueeze(1), c2w_cond), dim=1)
+    rel = (c2w_cond.inverse()[:, :, None] @ c2w[:, None]).transpose(1, 2)          # [B, T, C]: inv(c2w_cond[c]) @ c2w[t]
+    R, t = rel[..., :3, :3], rel[..., :3, 3:4]
+    Kinv = torch.inverse(K.float()[:, :, None])
+    return Kinv.transpose(-1, -2) @ torch.cross(t, R, dim=-2) @ Kinv

@@ -71,12 +71,14 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     if (d->rowbias && d->rows_per_group <= 0) return ERR_BAD_ARG;
     int bn = c2v_gemm_tile_n(d->N, d->epi);
     if (bn == 0) return ERR_UNSUPPORTED;
-    if (d->epi == C2V_EPI_LINEAR && d->splitk <= 1 && d->N % 64 == 0 && bn > 64) {
+    if (d->epi != C2V_EPI_GEGLU && d->splitk <= 1 && d->N % 64 == 0 && bn > 64) {
         // few output tiles and no split-K (shallow K): narrower N tiles put more CTAs (more TMA streams) on the machine
         const int mt = (d->M + 127) / 128;
         if (mt * ((d->N + bn - 1) / bn) < 120) bn = 64;
     }
     if (d->epi == C2V_EPI_GEGLU && (!d->out_bf16 || d->rowbias || d->residual)) return ERR_BAD_ARG;
+    if (d->epi == C2V_EPI_GELU && d->residual) return ERR_BAD_ARG;          // activation of the GEMM result only
+    if (d->epi < 0 || d->epi > C2V_EPI_GELU) return ERR_BAD_ARG;
 
     GemmKernelArgs a;
     memset(&a, 0, sizeof(a));
@@ -169,7 +171,7 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
         const uint32_t box[2] = {64, (uint32_t)bn};
         if (!make_tmap_bf16(&a.tmB, d->w, 2, dims, strides, box)) return ERR_TMA_ENCODE;
     }
-    if (d->epi == C2V_EPI_LINEAR && !a.cluster_reduce) {
+    if (d->epi != C2V_EPI_GEGLU && !a.cluster_reduce) {
         // TMA epilogue descriptors (residual load, output / split-K partial store).  When the output rows are not 16-byte
         // aligned (e.g. a 4-column bf16 output) the kernel falls back to its direct-store epilogue.
         const bool part = a.splits > 1;
@@ -301,7 +303,12 @@ int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int
 
 int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, int d, void* stream) {
     if (!F || !out) return ERR_BAD_ARG;
-    return epipolar_mask_launch(F, out, B, T, H, W, d, (cudaStream_t)stream);
+    return epipolar_mask_launch(F, out, B, T, T, H, W, d, (cudaStream_t)stream);
+}
+
+int c2v_epipolar_mask_rect(const float* F, uint8_t* out, int B, int T1, int T2, int H, int W, int d, void* stream) {
+    if (!F || !out) return ERR_BAD_ARG;
+    return epipolar_mask_launch(F, out, B, T1, T2, H, W, d, (cudaStream_t)stream);
 }
 
 // bitmap words of one query-tile row (64-key tiles) + 1 word holding the longest-first issue order

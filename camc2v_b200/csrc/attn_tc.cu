@@ -92,11 +92,7 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
 }
 
 template <int LOGW, int D>
-#if C2V_AT_MIN_CTAS == 3
-__global__ void __maxnreg__(112) attn_tc_kernel(const __grid_constant__ AttnKernelArgs p) {
-#else
 __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const __grid_constant__ AttnKernelArgs p) {
-#endif
     constexpr bool FAST = LOGW >= 3;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);

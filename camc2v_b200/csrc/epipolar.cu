@@ -9,17 +9,18 @@
 
 namespace c2v {
 
-__global__ void __launch_bounds__(256) epipolar_mask_kernel(const float* __restrict__ Fm, uint8_t* __restrict__ out, int T, int H, int W, int d,
-                                                            float thr, float off) {
+__global__ void __launch_bounds__(256) epipolar_mask_kernel(const float* __restrict__ Fm, uint8_t* __restrict__ out, int T1, int T, int H, int W,
+                                                            int d, float thr, float off) {
     // grid: x = query row (t1, i) of one batch element, y = batch.  Each warp sweeps key chunks of 16.
+    // F is [B, T1, T, 3, 3]: T1 query frames x T key frames (T1 = T in the UNet; 16 x (1 + n) for the adaptor's conditional mask)
     const int HW = H * W;
-    const int64_t L = (int64_t)T * HW;
+    const int64_t L = (int64_t)T * HW;            // keys per row
     const int b = blockIdx.y;
     const int row = blockIdx.x;
     const int t1 = row / HW, i = row % HW;
     const float xi = __fadd_rn(__fmul_rn((float)(i % W), (float)d), off);
     const float yi = __fadd_rn(__fmul_rn((float)(i / W), (float)d), off);
-    uint8_t* orow = out + ((size_t)b * L + row) * L;
+    uint8_t* orow = out + ((size_t)b * T1 * HW + row) * L;
     const int chunks = (int)(L / 16);
     for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
         const int key0 = c * 16;
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(256) epipolar_mask_kernel(const float* __restr
             const int t2 = (key0 + e) / HW;            // constant over the chunk whenever HW is a multiple of 16
             if (t2 != cur_t2) {
                 cur_t2 = t2;
-                const float* f = Fm + (((size_t)b * T + t1) * T + t2) * 9;
+                const float* f = Fm + (((size_t)b * T1 + t1) * T + t2) * 9;
                 const float a0 = __fmaf_rn(f[2], 1.0f, __fmaf_rn(f[1], yi, __fmul_rn(f[0], xi)));
                 const float a1 = __fmaf_rn(f[5], 1.0f, __fmaf_rn(f[4], yi, __fmul_rn(f[3], xi)));
                 const float a2 = __fmaf_rn(f[8], 1.0f, __fmaf_rn(f[7], yi, __fmul_rn(f[6], xi)));
@@ -50,12 +51,12 @@ __global__ void __launch_bounds__(256) epipolar_mask_kernel(const float* __restr
     }
 }
 
-int epipolar_mask_launch(const float* F, uint8_t* out, int B, int T, int H, int W, int d, cudaStream_t st) {
+int epipolar_mask_launch(const float* F, uint8_t* out, int B, int T1, int T, int H, int W, int d, cudaStream_t st) {
     const int HW = H * W;
-    if (((int64_t)T * HW) % 16 != 0 || B <= 0 || B > 65535) return ERR_UNSUPPORTED;
+    if (((int64_t)T * HW) % 16 != 0 || B <= 0 || B > 65535 || T1 <= 0) return ERR_UNSUPPORTED;
     const float thr = (float)((double)d * sqrt(2.0) / 2.0);
     const float off = (float)d / 2.0f - 0.5f;
-    epipolar_mask_kernel<<<dim3(T * HW, B), 256, 0, st>>>(F, out, T, H, W, d, thr, off);
+    epipolar_mask_kernel<<<dim3(T1 * HW, B), 256, 0, st>>>(F, out, T1, T, H, W, d, thr, off);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -201,10 +201,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                     tma_load_2d(smem + c * 16384, &p.tmR, &res_bar[c], n0 + c * 32, m0);
                 }
             }
-#ifndef C2V_EPI_FLUSH
-#define C2V_EPI_FLUSH 3
-#endif
-            const int flush = (!out_f32 && has_res) ? 1 : C2V_EPI_FLUSH;
+            const int flush = (!out_f32 && has_res) ? 1 : 3;
             int c_flushed = 0;
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
@@ -245,6 +242,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                         const float4 b4 = *reinterpret_cast<const float4*>(rb + nb + j);
                         f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                     }
+                }
+                if (p.epi == EPI_GELU && !part) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
                 }
                 if (out_f32) {
 #pragma unroll
@@ -350,6 +351,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                                 f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                             }
                         }
+                        if (p.epi == EPI_GELU && !part) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
+                        }
                         if (out_bf16) {
                             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + (size_t)m * ldo + n0 + c;
 #pragma unroll
@@ -371,6 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
                             if (bias) x += bias[n];
                             if (rb) x += rb[n];
                             if (resid) x += resid[(size_t)m * p.ldr + n];
+                            if (p.epi == EPI_GELU && !part) x = gelu_erf_f(x);
                             if (out_bf16)
                                 reinterpret_cast<__nv_bfloat16*>(outp)[(size_t)m * ldo + n] = __float2bfloat16(x);
                             else

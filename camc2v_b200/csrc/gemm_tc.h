@@ -6,7 +6,7 @@
 namespace c2v {
 
 enum AMode : int { A_PLAIN = 0, A_CONV2D = 1, A_CONVT = 2 };
-enum EpiMode : int { EPI_LINEAR = 0, EPI_GEGLU = 1 };
+enum EpiMode : int { EPI_LINEAR = 0, EPI_GEGLU = 1, EPI_GELU = 2 };   // GELU: linear epilogue + exact erf GELU (no residual)
 
 struct GemmKernelArgs {
     CUtensorMap tmA;        // activations (bf16): rank 2 [K, M] or rank 4 (C, W, H, N) / (C, HW, T, B)

@@ -30,7 +30,7 @@ int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, con
 int attention_temporal_launch(const void* qkv, void* out, int B, int T, int HW, int heads, cudaStream_t st);
 
 // epipolar.cu
-int epipolar_mask_launch(const float* F, uint8_t* out, int B, int T, int H, int W, int d, cudaStream_t st);
+int epipolar_mask_launch(const float* F, uint8_t* out, int B, int T1, int T2, int H, int W, int d, cudaStream_t st);
 int plucker_launch(const float* K, const float* c2w, float* out, int B, int T, int H, int W, int plucker, cudaStream_t st);
 
 }  // namespace c2v

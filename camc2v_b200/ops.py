@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import A_CONV2D, A_CONVT, A_PLAIN, EPI_GEGLU, EPI_LINEAR, AttnDesc, GemmDesc
+from ._lib import A_CONV2D, A_CONVT, A_PLAIN, EPI_GEGLU, EPI_GELU, EPI_LINEAR, AttnDesc, GemmDesc
 
 BF16 = _lib.operand_torch_dtype()      # the library's 16-bit operand type: bfloat16 (default build) or float16
 F32 = torch.float32
@@ -69,12 +69,15 @@ def _gemm(a, w, M, N, Cin, taps, a_mode, nb, d1, d2, lda, bias, rowbias, rows_pe
     return out
 
 
-def linear(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out=None, out_dtype=F32, rowbias=None, rows_per_group=0):
-    """a bf16 [M, K] (row stride may exceed K), w bf16 [N, K] -> [M, N] (+bias +rowbias +residual)."""
+def linear(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out=None, out_dtype=F32, rowbias=None, rows_per_group=0,
+           gelu: bool = False):
+    """a bf16 [M, K] (row stride may exceed K), w bf16 [N, K] -> [M, N] (+bias +rowbias +residual); gelu=True applies the exact
+    erf GELU to the result (the FeedForward of the adaptor, resampler.py:31-38)."""
     M, K = a.shape
     if a.stride(1) != 1 or w.stride(1) != 1 or w.stride(0) != K:
         raise _lib.C2VError("linear: operands must be K-contiguous")
-    return _gemm(a, w, M, w.shape[0], K, 1, A_PLAIN, 0, 0, 0, a.stride(0), bias, rowbias, rows_per_group, residual, out, out_dtype, EPI_LINEAR)
+    return _gemm(a, w, M, w.shape[0], K, 1, A_PLAIN, 0, 0, 0, a.stride(0), bias, rowbias, rows_per_group, residual, out, out_dtype,
+                 EPI_GELU if gelu else EPI_LINEAR)
 
 
 def geglu_linear(a: torch.Tensor, w_il: torch.Tensor, bias_il: torch.Tensor):
@@ -196,13 +199,13 @@ def attention_temporal(qkv: torch.Tensor, B: int, T: int, HW: int, heads: int):
 
 # ------------------------------------------------------------------------------------------------ camera
 def epipolar_mask(F: torch.Tensor, H: int, W: int, d: int) -> torch.Tensor:
-    """F fp32 [B,T,T,3,3] -> bool [B, T*H*W, T*H*W] (camcontexti2v.py:202-271), bit-exact."""
+    """F fp32 [B,T1,T2,3,3] -> bool [B, T1*H*W, T2*H*W] (camcontexti2v.py:202-271), bit-exact.  T1 = T2 for the UNet's temporal
+    blocks; T1 = 16 target frames x T2 = 1 + n context frames for the adaptor's conditional mask (camcontexti2v.py:493-521)."""
     _chk(F, F32, "epipolar_mask.F")
     F = F.contiguous()
-    B, T = F.shape[0], F.shape[1]
-    L = T * H * W
-    out = torch.empty((B, L, L), device=F.device, dtype=torch.uint8)
-    _lib.call("c2v_epipolar_mask", _p(F), _p(out), B, T, H, W, d, _stream())
+    B, T1, T2 = F.shape[0], F.shape[1], F.shape[2]
+    out = torch.empty((B, T1 * H * W, T2 * H * W), device=F.device, dtype=torch.uint8)
+    _lib.call("c2v_epipolar_mask_rect", _p(F), _p(out), B, T1, T2, H, W, d, _stream())
     return out.view(torch.bool)
 
 

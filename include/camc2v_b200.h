@@ -42,7 +42,7 @@ const char* c2v_status_string(int status);
  *   175-187, 68-70, 96, 386, 561-565; nn.Conv3d (3,1,1) of openaimodel3d.py:255-266.
  * ---------------------------------------------------------------------------------------------- */
 enum { C2V_A_PLAIN = 0, C2V_A_CONV2D = 1, C2V_A_CONVT = 2 };
-enum { C2V_EPI_LINEAR = 0, C2V_EPI_GEGLU = 1 };
+enum { C2V_EPI_LINEAR = 0, C2V_EPI_GEGLU = 1, C2V_EPI_GELU = 2 };   /* GELU: out = gelu_erf(A W^T + bias) (resampler.py:31-38) */
 
 typedef struct c2v_gemm_desc {
     const void* a;         /* bf16 activations.  PLAIN: [M, lda];  CONV2D: [nb, d2(H), d1(W), Cin];  CONVT: [nb(B), d2(T), d1(HW), Cin] */
@@ -145,6 +145,10 @@ int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int
  * ---------------------------------------------------------------------------------------------- */
 /* Materialise the epipolar mask (camcontexti2v.py:202-271): F fp32 [B,T,T,3,3] -> uint8 [B, T*H*W, T*H*W]. Bit-exact. */
 int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, int d, void* stream);
+/* Rectangular form: F fp32 [B,T1,T2,3,3] (T1 query frames, T2 key frames) -> uint8 [B, T1*H*W, T2*H*W]: the conditional mask
+ * between the 16 target frames and the 1 + n context frames that MultiLatentEpipolarAdaptor consumes
+ * (compute_conditional_epipolar_mask, camcontexti2v.py:493-521).  Bit-exact. */
+int c2v_epipolar_mask_rect(const float* F, uint8_t* out, int B, int T1, int T2, int H, int W, int d, void* stream);
 /* Conservative tile-occupancy bitmap of the epipolar mask for 128x64 (query, key) tiles of a square power-of-two grid
  * (W in {8,16,32}): map[b][q_tile][word] bit j = key tile j may contain an attended pair.  Words per row =
  * c2v_epipolar_tile_map_words(T,H,W); the LAST word of row r is not part of the bitmap: it holds the index of the query

@@ -39,19 +39,21 @@ def _load():
         _lib = ctypes.CDLL(_SO)
         _lib.epi_mask_oracle.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
         _lib.epi_mask_oracle.restype = None
+        _lib.epi_mask_oracle_rect.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+        _lib.epi_mask_oracle_rect.restype = None
         _lib.plucker_oracle.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
         _lib.plucker_oracle.restype = None
     return _lib
 
 
 def epipolar_mask(F: torch.Tensor, H: int, W: int, d: int) -> torch.Tensor:
-    """F [B,T,T,3,3] fp32 -> bool [B, T*H*W, T*H*W]  (camcontexti2v.py:202-271)."""
+    """F [B,T1,T2,3,3] fp32 -> bool [B, T1*H*W, T2*H*W]  (camcontexti2v.py:202-271; T1 = T2 in the UNet, T1 = 16 targets and
+    T2 = 1 + n context frames for the adaptor's conditional mask, camcontexti2v.py:493-521)."""
     lib = _load()
     Fm = np.ascontiguousarray(F.detach().cpu().numpy().astype(np.float32))
-    B, T = Fm.shape[0], Fm.shape[1]
-    L = T * H * W
-    out = np.empty((B, L, L), dtype=np.uint8)
-    lib.epi_mask_oracle(Fm.ctypes.data, B, T, H, W, d, out.ctypes.data)
+    B, T1, T2 = Fm.shape[0], Fm.shape[1], Fm.shape[2]
+    out = np.empty((B, T1 * H * W, T2 * H * W), dtype=np.uint8)
+    lib.epi_mask_oracle_rect(Fm.ctypes.data, B, T1, T2, H, W, d, out.ctypes.data)
     return torch.from_numpy(out).bool()
 
 

@@ -26,16 +26,18 @@ static inline float dot3_chain(float a0, float b0, float a1, float b1, float a2,
     return acc;
 }
 
-/* Fm: [B, T, T, 3, 3] fp32.  out: [B, T*HW, T*HW] uint8 (1 = attend), rows = (t1, pixel i), cols = (t2, pixel j). */
-void epi_mask_oracle(const float *Fm, int B, int T, int H, int W, int d, uint8_t *out) {
+/* Fm: [B, T1, T2, 3, 3] fp32.  out: [B, T1*HW, T2*HW] uint8 (1 = attend), rows = (t1, pixel i), cols = (t2, pixel j).
+ * T1 = T2 for the UNet's temporal blocks; T1 = 16 target frames, T2 = 1 + n context frames for the adaptor's conditional mask
+ * (compute_conditional_epipolar_mask, R/model/camcontexti2v.py:493-521). */
+void epi_mask_oracle_rect(const float *Fm, int B, int T1, int T2, int H, int W, int d, uint8_t *out) {
     const int HW = H * W;
-    const size_t L = (size_t)T * HW;
+    const size_t L2 = (size_t)T2 * HW;
     const float thr = (float)((double)d * sqrt(2.0) / 2.0);
     const float off = (float)d / 2.0f - 0.5f;
     for (int b = 0; b < B; ++b)
-        for (int t1 = 0; t1 < T; ++t1)
-            for (int t2 = 0; t2 < T; ++t2) {
-                const float *f = Fm + (((size_t)b * T + t1) * T + t2) * 9;
+        for (int t1 = 0; t1 < T1; ++t1)
+            for (int t2 = 0; t2 < T2; ++t2) {
+                const float *f = Fm + (((size_t)b * T1 + t1) * T2 + t2) * 9;
                 for (int i = 0; i < HW; ++i) {
                     const float xi = (float)(i % W) * (float)d + off;
                     const float yi = (float)(i / W) * (float)d + off;
@@ -48,7 +50,7 @@ void epi_mask_oracle(const float *Fm, int B, int T, int H, int W, int d, uint8_t
                     l0 = l0 / nrm;
                     l1 = l1 / nrm;
                     l2 = l2 / nrm;
-                    uint8_t *row = out + ((size_t)b * L + (size_t)t1 * HW + i) * L + (size_t)t2 * HW;
+                    uint8_t *row = out + (((size_t)b * T1 + t1) * HW + i) * L2 + (size_t)t2 * HW;
                     for (int j = 0; j < HW; ++j) {
                         const float xj = (float)(j % W) * (float)d + off;
                         const float yj = (float)(j / W) * (float)d + off;
@@ -58,6 +60,8 @@ void epi_mask_oracle(const float *Fm, int B, int T, int H, int W, int d, uint8_t
                 }
             }
 }
+
+void epi_mask_oracle(const float *Fm, int B, int T, int H, int W, int d, uint8_t *out) { epi_mask_oracle_rect(Fm, B, T, T, H, W, d, out); }
 
 /*
  * K: [B, T, 3, 3], c2w: [B, T, 4, 4] -> out [B, 6, T, H, W].

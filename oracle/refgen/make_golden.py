@@ -238,6 +238,54 @@ def gen_variants(check):
     np.savez_compressed(os.path.join(GOLD, "variants.npz"), **out)
 
 
+def gen_adaptor(check):
+    """MultiLatentEpipolarAdaptor (SURVEY f-1) + conditional epipolar mask, reduced size: 8x8 latents, 2 context frames."""
+    import json
+    rh.setup_reference_imports()
+    from model.modules.adaptors import MultiLatentEpipolarAdaptor
+    kw = dict(query_dim=128, num_queries=64, video_length=16, embedding_dim=4, output_dim=4, depth=2, checkpoint=False,
+              timestep_embedding_type="sinusoidal_embedded", use_plucker_embedding=False)
+    torch.manual_seed(0)
+    ref = MultiLatentEpipolarAdaptor(**kw).eval()
+    synth.fill_module_(ref, seed=5)
+    model = build_ref(SMALL_UNET, 128)                       # only for its (bound) camera-geometry methods
+    hw_img, h = 64, 8
+    K, w2c = synth.synth_camera("pan_yaw", T=16, H=hw_img, W=hw_img, B=1)
+    _, w2c_o = synth.synth_camera("orbit", T=16, H=hw_img, W=hw_img, B=1)
+    w2c_cond = w2c_o[:, [5, 11]].contiguous()                # two additional context views
+    cond_idx = torch.zeros(1, dtype=torch.long)
+    # compute_conditional_epipolar_mask (camcontexti2v.py:493-521) with the batch look-ups replaced by the tensors themselves
+    from einops import rearrange, repeat
+    c2w, c2w_cond = w2c.float().inverse(), w2c_cond.float().inverse()
+    c2w_cond = torch.cat((c2w[torch.arange(1), cond_idx].unsqueeze(1), c2w_cond), dim=1)
+    rel = model.get_pairwise_relative_pose(c2w_cond, c2w)
+    rel = rearrange(rel, "B T C H W -> B C T H W")
+    R, t = rel[..., :3, :3], rel[..., :3, 3:4]
+    C = R.shape[2]
+    Kr = repeat(K.float(), "B T H W -> B (T C) H W", C=C)
+    Fm = model.get_fundamental_matrix(Kr, rearrange(R, "B T C H W -> B (T C) H W"), rearrange(t, "B T C H W -> B (T C) H W"))
+    Fm = rearrange(Fm, "B (T C) H W -> B T C H W", C=C)
+    mask = model.get_epipolar_mask(Fm, 16, h, h, 8, True)
+    z = synth.synth_tensor("adaptor.z", (1, C * h * h, 4), 9)
+    with torch.no_grad():
+        y = ref(z, mask)
+        y_nomask = ref(z, None)
+    print(f"  adaptor: mask {tuple(mask.shape)} density {mask.float().mean():.4f}, out std {y.std():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "adaptor_small.npz"), K=K.numpy(), w2c=w2c.numpy(), w2c_cond=w2c_cond.numpy(), F=Fm.numpy(),
+                        mask_packed=np.packbits(mask.numpy(), axis=-1), y=y.numpy(), y_nomask=y_nomask.numpy(),
+                        kwargs=json.dumps(kw))
+    json.dump({k: list(v.shape) for k, v in ref.state_dict().items()}, open(os.path.join(GOLD, "state_dict_adaptor.json"), "w"), indent=0)
+    if check:
+        import oracle
+        from oracle import adaptor_oracle
+        sd = ref.state_dict()
+        Fo = adaptor_oracle.conditional_fundamental_matrices(K, w2c, w2c_cond, cond_idx)
+        mo = oracle.epipolar_mask(Fo, h, h, 8)
+        yo = adaptor_oracle.adaptor_forward(sd, z, mo, depth=2)
+        print(f"    oracle F bit-identical: {bool(torch.equal(Fo, Fm))}; mask identical: {bool(torch.equal(mo, mask))}; "
+              f"y rel-L2 {rel_err(yo, y)[0]:.3e}")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -254,6 +302,9 @@ if __name__ == "__main__":
     if a.only in (None, "variants"):
         print("[variants]")
         gen_variants(a.check_oracle)
+    if a.only in (None, "adaptor"):
+        print("[adaptor]")
+        gen_adaptor(a.check_oracle)
     if a.only in ("unet_full",):
         print("[unet_full]")
         gen_unet_full(a.check_oracle)

@@ -1,0 +1,57 @@
+"""GPU parity of the once-per-sample MultiLatentEpipolarAdaptor against the golden outputs of the
+unmodified reference classes (tests/golden/adaptor_small.npz: adaptors.py:36-182 + the conditional mask of
+camcontexti2v.py:493-521).  Mask bit-exact; adaptor output within the tolerance of tests/test_unet_gpu.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+TOL = float(os.environ.get("C2V_TEST_TOL", "5e-3"))
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / b.norm()), float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(os.path.join(GOLD, "adaptor_small.npz"))
+    return g, json.loads(str(g["kwargs"]))
+
+
+def test_conditional_mask_bit_exact(gold):
+    from camc2v_b200 import camera, ops
+    g, _ = gold
+    K, w2c, w2c_cond = (torch.from_numpy(g[k]) for k in ("K", "w2c", "w2c_cond"))
+    Fm = camera.conditional_fundamental_matrices(K, w2c, w2c_cond, torch.zeros(1, dtype=torch.long))
+    assert np.allclose(Fm.numpy(), g["F"], rtol=1e-5, atol=1e-7)
+    m = ops.epipolar_mask(torch.from_numpy(g["F"]).to(DEV), 8, 8, 8)                  # rectangular: 16 target x 3 context frames
+    assert m.shape == (1, 1024, 192)
+    assert np.array_equal(np.packbits(m.cpu().numpy(), axis=-1), g["mask_packed"])
+
+
+def test_adaptor_vs_reference_golden(gold):
+    from camc2v_b200 import ops, synth
+    from camc2v_b200.adaptor import MultiLatentEpipolarAdaptor
+    g, kw = gold
+    m = MultiLatentEpipolarAdaptor(**kw)
+    synth.fill_module_(m, seed=5)
+    m = m.to(DEV)
+    mask = ops.epipolar_mask(torch.from_numpy(g["F"]).to(DEV), 8, 8, 8)
+    z = synth.synth_tensor("adaptor.z", (1, 192, 4), 9).to(DEV)
+    for key, mk in (("y", mask), ("y_nomask", None)):
+        y = m(z, mk)
+        assert y.shape == (1, 1024, 4) and torch.isfinite(y).all()
+        l2, mx = rel(y, torch.from_numpy(g[key]))
+        print(f"adaptor {key}: rel-L2 {l2:.3e} max-norm {mx:.3e}")
+        # the last op is a LayerNorm over only output_dim = 4 channels, which amplifies the worst element: 2x bound on the max-norm
+        assert l2 < TOL and mx < 2 * TOL, (key, l2, mx)
+    # batch of two = two independent samples
+    y2 = m(torch.cat([z, z.flip(1)], 0), torch.cat([mask, mask], 0))
+    assert rel(y2[0], m(z, mask)[0])[0] < TOL

@@ -28,4 +28,5 @@ def test_bf16_build_kernels():
 
 
 def test_bf16_build_unet_parity_at_2e_2():
-    _run(["tests/test_unet_gpu.py", "-k", "golden or 25_step or cfg_step or mask_format or deterministic"], "2e-2")
+    _run(["tests/test_unet_gpu.py", "tests/test_adaptor_gpu.py", "-k", "golden or 25_step or cfg_step or mask_format or deterministic or adaptor"],
+         "2e-2")

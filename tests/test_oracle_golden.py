@@ -181,3 +181,41 @@ def test_variant_oracles_match_reference_baselines(variant):
     y = UNetOracle(sd, cfg).forward(xc, t, inp["ctx_uncond"], inp["fs"], cam)
     l2, mx = _rel(y, torch.from_numpy(g[f"{variant}.y"]))
     assert l2 < 1e-5 and mx < 1e-5, (l2, mx)
+
+
+# ------------------------------------------------------------------------------------------------ adaptor (SURVEY f-1)
+def _adaptor_gold():
+    import json
+    g = np.load(os.path.join(GOLD, "adaptor_small.npz"))
+    return g, json.loads(str(g["kwargs"]))
+
+
+def test_adaptor_conditional_mask_bit_exact():
+    """compute_conditional_epipolar_mask (camcontexti2v.py:493-521): F between 16 target and 1 + 2 context frames, rectangular mask."""
+    from oracle import adaptor_oracle
+    g, _ = _adaptor_gold()
+    K, w2c, w2c_cond = (torch.from_numpy(g[k]) for k in ("K", "w2c", "w2c_cond"))
+    Fm = adaptor_oracle.conditional_fundamental_matrices(K, w2c, w2c_cond, torch.zeros(1, dtype=torch.long))
+    if not np.array_equal(Fm.numpy(), g["F"]):
+        assert np.allclose(Fm.numpy(), g["F"], rtol=1e-5, atol=1e-7)       # LAPACK inverse may round differently on another host
+        Fm = torch.from_numpy(g["F"])
+    m = oracle.epipolar_mask(Fm, 8, 8, 8)
+    assert m.shape == (1, 16 * 64, 3 * 64)
+    assert np.array_equal(np.packbits(m.numpy(), axis=-1), g["mask_packed"])
+
+
+def test_adaptor_oracle_matches_reference():
+    from camc2v_b200.adaptor import MultiLatentEpipolarAdaptor
+    from oracle import adaptor_oracle
+    g, kw = _adaptor_gold()
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in MultiLatentEpipolarAdaptor(**kw).state_dict().items()}
+    import json
+    assert {k: list(v) for k, v in shapes.items()} == json.load(open(os.path.join(GOLD, "state_dict_adaptor.json")))   # drop-in state_dict
+    sd = synth.synth_state_dict(shapes, 5)
+    mask = torch.from_numpy(np.unpackbits(g["mask_packed"], axis=-1)[..., :192].astype(bool))
+    z = synth.synth_tensor("adaptor.z", (1, 192, 4), 9)
+    for key, m in (("y", mask), ("y_nomask", None)):
+        y = adaptor_oracle.adaptor_forward(sd, z, m, depth=kw["depth"])
+        l2, mx = _rel(y, torch.from_numpy(g[key]))
+        assert l2 < 1e-5 and mx < 1e-5, (key, l2, mx)
