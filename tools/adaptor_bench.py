@@ -1,0 +1,76 @@
+"""Once-per-sample MultiLatentEpipolarAdaptor at the shipped size (camcontexti2v_256.yaml:141-152:
+query_dim 512, depth 12, 16 x 1024 queries, 1 reference + 2 context frames = 3072 context tokens) on one B200, plus the
+conditional mask build; the CPU oracle (port of the reference) is timed on ONE layer-pair-sized sample and scaled by depth.
+
+    python tools/adaptor_bench.py [--no-cpu]
+Prints one JSON line.  CUDA events on the launching stream, 2 warm-up + 5 timed forwards.
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+from camc2v_b200 import camera, ops, synth  # noqa: E402
+from camc2v_b200.adaptor import MultiLatentEpipolarAdaptor  # noqa: E402
+
+KW = dict(query_dim=512, num_queries=1024, video_length=16, embedding_dim=4, output_dim=4, depth=12, checkpoint=True,
+          timestep_embedding_type="sinusoidal_embedded", use_plucker_embedding=False)
+
+
+def flops(depth, Lq, Lk, D, inner=512, ff=4):
+    per = 2 * Lq * D * inner + 2 * (Lk + 2) * D * 2 * inner + 4 * Lq * (Lk + 2) * inner + 2 * Lq * inner * D + 2 * 2 * Lq * D * ff * D
+    return depth * per
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    m = MultiLatentEpipolarAdaptor(**KW)
+    synth.fill_module_(m, seed=5)
+    m = m.to(dev)
+    K, w2c = synth.synth_camera("pan_yaw", T=16, B=1)
+    _, w2c_o = synth.synth_camera("orbit", T=16, B=1)
+    w2c_cond = w2c_o[:, [5, 11]].contiguous()
+    z = synth.synth_tensor("adaptor.z", (1, 3 * 1024, 4), 9).to(dev)
+
+    def build_mask():
+        Fm = camera.conditional_fundamental_matrices(K, w2c, w2c_cond, torch.zeros(1, dtype=torch.long)).to(dev)
+        return ops.epipolar_mask(Fm, 32, 32, 8)
+
+    mask = build_mask()
+    for _ in range(2):
+        y = m(z, mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        y = m(z, mask)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    t0 = time.perf_counter()
+    for _ in range(5):
+        build_mask()
+    torch.cuda.synchronize()
+    ms_mask = (time.perf_counter() - t0) / 5 * 1e3
+    fl = flops(12, 16384, 3072, 512)
+    line = {"metric": "adaptor_ms_per_sample", "value": ms, "unit": "ms (MultiLatentEpipolarAdaptor forward, 16384 queries x 3072 context tokens, depth 12)",
+            "mask_build_ms": ms_mask, "mask_density": float(mask.float().mean()), "algorithmic_tflop": fl / 1e12,
+            "tflops": fl / ms / 1e9, "finite": bool(torch.isfinite(y).all()), "dtype": ops._lib.OPERANDS}
+    if "--no-cpu" not in sys.argv:
+        from oracle import adaptor_oracle
+        sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+        zc, mc = z.cpu(), mask.cpu()
+        t0 = time.perf_counter()
+        adaptor_oracle.adaptor_forward(sd, zc, mc, depth=1)
+        s1 = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": s1 * 12 * 1e3, "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"oracle (CPU port of the reference, fp32) on 1 of the 12 layers: {s1:.2f} s, scaled x12"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
