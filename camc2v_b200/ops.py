@@ -115,6 +115,18 @@ def conv_t3(a: torch.Tensor, w: torch.Tensor, B: int, T: int, HW: int, bias=None
     return _gemm(a, w, B * T * HW, w.shape[0], Cin, 3, A_CONVT, B, HW, T, Cin, bias, None, 0, residual, None, out_dtype, EPI_LINEAR)
 
 
+def copy_rows(src: torch.Tensor, dst: torch.Tensor):
+    """dst[r, :] = src[r, :] for 16-bit operand tensors: src [rows, C] contiguous, dst a [rows, C] view whose rows may be strided
+    (e.g. a row slice of a wider / longer buffer: concatenation along the token axis without a torch.cat temporary)."""
+    _chk(src, BF16, "copy_rows.src")
+    _chk(dst, BF16, "copy_rows.dst")
+    rows, C_ = src.shape
+    if not src.is_contiguous() or tuple(dst.shape) != (rows, C_) or dst.stride(1) != 1:
+        raise _lib.C2VError("copy_rows: src must be contiguous [rows, C], dst a row-strided view of the same shape")
+    _lib.call("c2v_copy_rows", _p(src), _p(dst), rows, C_, 1, 0, dst.stride(0), _stream())
+    return dst
+
+
 def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias, silu_in: bool):
     _chk(x, F32, "skinny_linear.x")
     _chk(w, BF16, "skinny_linear.w")

@@ -286,6 +286,28 @@ def gen_adaptor(check):
               f"y rel-L2 {rel_err(yo, y)[0]:.3e}")
 
 
+def gen_resampler(check):
+    """Resampler image-token projector (SURVEY f-4), reduced size."""
+    import json
+    rh.setup_reference_imports()
+    from lvdm.modules.encoders.resampler import Resampler
+    kw = dict(dim=128, depth=2, dim_head=64, heads=4, num_queries=4, embedding_dim=96, output_dim=128, ff_mult=4, video_length=16,
+              use_timestep_emb=True)
+    torch.manual_seed(0)
+    ref = Resampler(**kw).eval()
+    synth.fill_module_(ref, seed=6)
+    x = synth.synth_tensor("resampler.x", (2, 33, 96), 10)
+    with torch.no_grad():
+        y = ref(x)
+    print(f"  resampler: out {tuple(y.shape)} std {y.std():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "resampler_small.npz"), y=y.numpy(), kwargs=json.dumps(kw))
+    json.dump({k: list(v.shape) for k, v in ref.state_dict().items()}, open(os.path.join(GOLD, "state_dict_resampler.json"), "w"), indent=0)
+    if check:
+        from oracle import resampler_oracle
+        yo = resampler_oracle.resampler_forward(ref.state_dict(), x, depth=2, heads=4)
+        print(f"    oracle vs reference: rel-L2 {rel_err(yo, y)[0]:.3e}")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -305,6 +327,9 @@ if __name__ == "__main__":
     if a.only in (None, "adaptor"):
         print("[adaptor]")
         gen_adaptor(a.check_oracle)
+    if a.only in (None, "resampler"):
+        print("[resampler]")
+        gen_resampler(a.check_oracle)
     if a.only in ("unet_full",):
         print("[unet_full]")
         gen_unet_full(a.check_oracle)

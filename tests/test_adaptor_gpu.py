@@ -55,3 +55,20 @@ def test_adaptor_vs_reference_golden(gold):
     # batch of two = two independent samples
     y2 = m(torch.cat([z, z.flip(1)], 0), torch.cat([mask, mask], 0))
     assert rel(y2[0], m(z, mask)[0])[0] < TOL
+
+
+def test_resampler_vs_reference_golden():
+    """Resampler image-token projector (SURVEY f-4, resampler.py:100-166) against the unmodified reference class."""
+    from camc2v_b200 import synth
+    from camc2v_b200.resampler import Resampler
+    g = np.load(os.path.join(GOLD, "resampler_small.npz"))
+    kw = json.loads(str(g["kwargs"]))
+    m = Resampler(**kw)
+    synth.fill_module_(m, seed=6)
+    m = m.to(DEV)
+    x = synth.synth_tensor("resampler.x", (2, 33, 96), 10).to(DEV)
+    y = m(x)
+    assert y.shape == (2, 64, 128) and torch.isfinite(y).all()
+    l2, mx = rel(y, torch.from_numpy(g["y"]))
+    print(f"resampler: rel-L2 {l2:.3e} max-norm {mx:.3e}")
+    assert l2 < TOL and mx < 2 * TOL, (l2, mx)

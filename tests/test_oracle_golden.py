@@ -219,3 +219,20 @@ def test_adaptor_oracle_matches_reference():
         y = adaptor_oracle.adaptor_forward(sd, z, m, depth=kw["depth"])
         l2, mx = _rel(y, torch.from_numpy(g[key]))
         assert l2 < 1e-5 and mx < 1e-5, (key, l2, mx)
+
+
+# ------------------------------------------------------------------------------------------------ resampler (SURVEY f-4)
+def test_resampler_oracle_matches_reference():
+    import json
+    from camc2v_b200.resampler import Resampler
+    from oracle import resampler_oracle
+    g = np.load(os.path.join(GOLD, "resampler_small.npz"))
+    kw = json.loads(str(g["kwargs"]))
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in Resampler(**kw).state_dict().items()}
+    assert {k: list(v) for k, v in shapes.items()} == json.load(open(os.path.join(GOLD, "state_dict_resampler.json")))   # drop-in state_dict
+    sd = synth.synth_state_dict(shapes, 6)
+    x = synth.synth_tensor("resampler.x", (2, 33, 96), 10)
+    y = resampler_oracle.resampler_forward(sd, x, depth=kw["depth"], heads=kw["heads"])
+    l2, mx = _rel(y, torch.from_numpy(g["y"]))
+    assert l2 < 1e-5 and mx < 1e-5, (l2, mx)

@@ -72,5 +72,39 @@ def main():
     print(json.dumps(line))
 
 
+def resampler_main():
+    """Resampler at the shipped size (camcontexti2v_256.yaml:110-122): 257 CLIP tokens of one frame -> 256 context tokens."""
+    from camc2v_b200.resampler import Resampler
+    dev = torch.device("cuda", 0)
+    kw = dict(dim=1024, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=1024, ff_mult=4, video_length=16,
+              use_timestep_emb=True)
+    m = Resampler(**kw)
+    synth.fill_module_(m, seed=6)
+    m = m.to(dev)
+    x = synth.synth_tensor("resampler.x", (3, 257, 1280), 10).to(dev)          # reference frame + 2 context frames
+    for _ in range(2):
+        y = m(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        y = m(x)
+    e1.record()
+    torch.cuda.synchronize()
+    line = {"metric": "resampler_ms_per_sample", "value": e0.elapsed_time(e1) / 10, "unit": "ms (Resampler forward, 3 frames x 257 CLIP tokens -> 3 x 256 x 1024)",
+            "finite": bool(torch.isfinite(y).all()), "dtype": ops._lib.OPERANDS}
+    if "--no-cpu" not in sys.argv:
+        from oracle import resampler_oracle
+        sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+        t0 = time.perf_counter()
+        resampler_oracle.resampler_forward(sd, x.cpu(), depth=4, heads=12)
+        line["cpu_baseline"] = {"value": (time.perf_counter() - t0) * 1e3, "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "oracle (CPU port of the reference, fp32), whole forward"}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
-    main()
+    if "--resampler" in sys.argv:
+        resampler_main()
+    else:
+        main()
