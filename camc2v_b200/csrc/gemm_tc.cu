@@ -34,8 +34,10 @@ struct GemmSmem {
     static constexpr int total(int stages) { return stages * STAGE_BYTES + 256 + 1024; }  // + barriers/tmem ptr + 1024B alignment slack
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmKernelArgs p) {
+// EPI_WARPS = 4 everywhere except the GEGLU projections, whose erf epilogue (2x the main loop's time at K = 320) is split over
+// two warps per TMEM lane quarter (EPI_WARPS = 8, 320 threads): warps 2..5 take the even 16-column chunks, warps 6..9 the odd ones.
+template <int BN, int EPI_WARPS = 4>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 2) gemm_tc_kernel(const __grid_constant__ GemmKernelArgs p) {
     using S = GemmSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -165,7 +167,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
         const float* rb = (!part && p.rowbias && row_ok) ? p.rowbias + (size_t)(m / p.rows_per_group) * p.N : nullptr;
         const float* bias = part ? nullptr : p.bias;
-        if (part && p.cluster_reduce) {
+        if (EPI_WARPS > 4 && (warp >= 6) && p.epi != EPI_GEGLU) {
+            // the second epilogue group only exists for the GEGLU epilogue
+        } else if (part && p.cluster_reduce) {
             // ---- split-K inside a thread-block cluster: park the raw fp32 partial tile in (now idle) pipeline smem, in the
             //      same conflict-free chunk-major swizzled layout as the TMA staging; the reduction follows the cluster barrier
             mbar_wait<200>(acc_bar, 0);
@@ -287,8 +291,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             constexpr int HALF = BN / 2;
             const int no = blockIdx.y * HALF;          // output column base
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + no;
+            constexpr int NGRP = EPI_WARPS / 4;
+            const int grp = (warp - 2) >> 2;
 #pragma unroll 1
-            for (int c = 0; c < HALF; c += 16) {
+            for (int c = grp * 16; c < HALF; c += 16 * NGRP) {
                 uint32_t xv[16], gv[16];
                 tmem_ld16(trow + c, xv);
                 tmem_ld16(trow + HALF + c, gv);
@@ -441,12 +447,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     }
 }
 
-template <int BN>
+template <int BN, int EPI_WARPS = 4>
 static int launch(const GemmKernelArgs& a, int m_tiles, int n_tiles, cudaStream_t st) {
+    constexpr int THREADS = 64 + 32 * EPI_WARPS;
     using S = GemmSmem<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        C2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        C2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     // Ring depth: a grid that puts at most one CTA on an SM has the whole 227 KB to itself and is latency-bound on the
@@ -466,7 +473,7 @@ static int launch(const GemmKernelArgs& a, int m_tiles, int n_tiles, cudaStream_
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(m_tiles, n_tiles, a.splits);
-        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.blockDim = dim3(THREADS);
         cfg.dynamicSmemBytes = S::total(stages);
         cfg.stream = st;
         cudaLaunchAttribute at[1];
@@ -476,10 +483,10 @@ static int launch(const GemmKernelArgs& a, int m_tiles, int n_tiles, cudaStream_
         at[0].val.clusterDim.z = a.splits;          // the K splits of one output tile are one cluster
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        C2V_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, b));
+        C2V_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI_WARPS>, b));
         return OK;
     }
-    gemm_tc_kernel<BN><<<dim3(m_tiles, n_tiles, a.splits), GEMM_THREADS, S::total(stages), st>>>(b);
+    gemm_tc_kernel<BN, EPI_WARPS><<<dim3(m_tiles, n_tiles, a.splits), THREADS, S::total(stages), st>>>(b);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
@@ -530,6 +537,15 @@ int splitk_reduce_launch(const float* ws, int splits, int M, int N, const float*
 }
 
 int gemm_tc_launch(const GemmKernelArgs& a, int bn, int m_tiles, int n_tiles, cudaStream_t st) {
+    if (a.epi == EPI_GEGLU) {      // two epilogue warp groups for the erf epilogue (-10 % on the 32x32-level FF projection)
+        switch (bn) {
+            case 64: return launch<64, 8>(a, m_tiles, n_tiles, st);
+            case 128: return launch<128, 8>(a, m_tiles, n_tiles, st);
+            case 160: return launch<160, 8>(a, m_tiles, n_tiles, st);
+            case 256: return launch<256, 8>(a, m_tiles, n_tiles, st);
+            default: return ERR_UNSUPPORTED;
+        }
+    }
     switch (bn) {
         case 64: return launch<64>(a, m_tiles, n_tiles, st);
         case 128: return launch<128>(a, m_tiles, n_tiles, st);
