@@ -1,6 +1,7 @@
 // extern "C" surface of libcamc2v_b200.so (declared in include/camc2v_b200.h).
 // Argument validation, TMA descriptor construction and kernel dispatch; no allocation, no sync.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/camc2v_b200.h"
 #include "attn_tc.h"
@@ -238,6 +239,13 @@ int c2v_attention(const c2v_attn_desc* d, void* stream) {
     if (d->bq <= 0 || d->lq <= 0 || d->lk <= 0 || d->heads <= 0 || d->kv_div <= 0) return ERR_BAD_ARG;
     if (d->heads > 65535 || d->bq > 65535) return ERR_UNSUPPORTED;
     if ((d->ldq | d->ldk | d->ldv | d->ldo) % 8 != 0) return ERR_UNSUPPORTED;
+    if (!d->epi_F && !d->mask && !d->k2 && !d->v2 && d->lk2 <= 0 && d->lk <= 128) {
+        // short key sequences (text / per-frame image cross-attention, self-attention of the 8x8 / 4x4 levels): all of K and V fit
+        // in shared memory (measured: faster up to 128 keys, slower at 256 where every 128-query CTA would re-stage 74 KB), warp-level mma.sync kernel (attn_small.cu) instead of the 128 x 64 tcgen05 tile pipeline
+        return attn_small_launch(d->q, d->k, d->v, d->out, d->bq, d->lq, d->lk, d->heads, d->kv_div, d->ldq, d->ldk, d->ldv, d->ldo,
+                                 d->q_bstride, d->k_bstride, d->v_bstride, d->o_bstride, 0.125f * 1.4426950408889634f, d->out_scale,
+                                 d->accumulate, (cudaStream_t)stream);
+    }
     AttnKernelArgs a;
     memset(&a, 0, sizeof(a));
     const int hd = d->heads * 64;
