@@ -120,9 +120,13 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     } else if (d->a_mode == C2V_A_CONV2D) {
         const int W = d->d1, H = d->d2, NB = d->nb;
         if (W <= 0 || H <= 0 || NB <= 0 || d->M != NB * H * W) return ERR_BAD_ARG;
-        if (W > 128 || 128 % W != 0) return ERR_UNSUPPORTED;
-        int bh, bnimg;
-        if (W * H >= 128) {
+        if (W > 128 ? (W % 128 != 0) : (128 % W != 0)) return ERR_UNSUPPORTED;
+        int bh, bnimg, bw = W;
+        if (W > 128) {             // wide images (VAE decoder, 256 x 256): one tile = 128 consecutive pixels of one image row
+            bw = 128;
+            bh = 1;
+            bnimg = 1;
+        } else if (W * H >= 128) {
             if ((W * H) % 128 != 0) return ERR_UNSUPPORTED;
             bh = 128 / W;
             bnimg = 1;
@@ -135,11 +139,11 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
         }
         const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
         const uint64_t strides[3] = {(uint64_t)d->Cin * 2, (uint64_t)W * d->Cin * 2, (uint64_t)H * W * d->Cin * 2};
-        const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)bh, (uint32_t)bnimg};
+        const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
         if (!make_tmap_bf16(&a.tmA, d->a, 4, dims, strides, box)) return ERR_TMA_ENCODE;
         a.dim1 = W;
         a.dim2 = H;
-        a.tile_rows = W * bh * bnimg;
+        a.tile_rows = bw * bh * bnimg;
     } else if (d->a_mode == C2V_A_CONVT) {
         const int HW = d->d1, T = d->d2, B = d->nb;
         if (HW <= 0 || T <= 0 || B <= 0 || d->M != B * T * HW) return ERR_BAD_ARG;
@@ -233,6 +237,11 @@ int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* o
 }
 
 int c2v_epipolar_tile_map_words(int T, int H, int W);
+
+int c2v_softmax_rows(const float* x, void* out, int rows, int n, float scale, void* stream) {
+    if (!x || !out) return ERR_BAD_ARG;
+    return softmax_rows_launch(x, out, rows, n, scale, (cudaStream_t)stream);
+}
 
 int c2v_attention(const c2v_attn_desc* d, void* stream) {
     if (!d || !d->q || !d->k || !d->v || !d->out) return ERR_BAD_ARG;

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 2) gemm_tc_kernel(const _
                 const int hw = p.dim1 * p.dim2;
                 c3 = m0 / hw;
                 c2 = (m0 % hw) / p.dim1;
-                c1 = 0;
+                c1 = (m0 % hw) % p.dim1;           // 0 unless the image is wider than a tile (then a multiple of 128)
             } else {                                    // A_CONVT: rows ordered (b, t, p)
                 const int thw = p.dim1 * p.dim2;
                 c3 = m0 / thw;

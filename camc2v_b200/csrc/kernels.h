@@ -12,6 +12,8 @@ int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta,
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32,
                      int rows, int C, float eps, cudaStream_t st);
 
+int softmax_rows_launch(const float* x, void* out, int rows, int n, float scale, cudaStream_t st);
+
 // elementwise.cu
 int to_channels_last_launch(const float* in, void* out, int B, int C, int S, int Cpad, int out_bf16, cudaStream_t st);
 int from_channels_last_launch(const float* in, float* out, int B, int C, int S, cudaStream_t st);

@@ -281,4 +281,45 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
     return OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row softmax: out[r, :] = softmax(scale * x[r, :]) as 16-bit operands.  One warp per row, fp32 statistics.
+// Used by the single-head, 512-wide attention block of the VAE decoder (R/lvdm/modules/networks/ae_modules.py:53-80), whose
+// head dim does not fit the 64-wide flash kernels: scores and P.V go through the GEMM kernel, the softmax through this one.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int n,
+                                                           float scale_log2) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (size_t)row * n;
+    float mx = -INFINITY;
+    for (int i = lane * 4; i < n; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float m = mx * scale_log2;
+    float sum = 0.f;
+    for (int i = lane * 4; i < n; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        sum += (fast_exp2(fmaf(v.x, scale_log2, -m)) + fast_exp2(fmaf(v.y, scale_log2, -m))) +
+               (fast_exp2(fmaf(v.z, scale_log2, -m)) + fast_exp2(fmaf(v.w, scale_log2, -m)));
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* o = out + (size_t)row * n;
+    for (int i = lane * 4; i < n; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        *reinterpret_cast<uint2*>(o + i) = make_uint2(pack_bf16(fast_exp2(fmaf(v.x, scale_log2, -m)) * inv, fast_exp2(fmaf(v.y, scale_log2, -m)) * inv),
+                                                      pack_bf16(fast_exp2(fmaf(v.z, scale_log2, -m)) * inv, fast_exp2(fmaf(v.w, scale_log2, -m)) * inv));
+    }
+}
+
+int softmax_rows_launch(const float* x, void* out, int rows, int n, float scale, cudaStream_t st) {
+    if (rows <= 0 || n <= 0 || n % 4 != 0) return ERR_UNSUPPORTED;
+    softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(out), rows, n, scale * 1.4426950408889634f);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
 }  // namespace c2v

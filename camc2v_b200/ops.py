@@ -154,6 +154,16 @@ def groupnorm(x: torch.Tensor, gamma, beta, ns: int, rows: int, eps: float, silu
     return out
 
 
+def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """softmax(scale * x) over the last dim: fp32 [rows, n] -> 16-bit operands [rows, n]."""
+    _chk(x, F32, "softmax_rows.x")
+    if not x.is_contiguous() or x.dim() != 2:
+        raise _lib.C2VError("softmax_rows: x must be a contiguous [rows, n] matrix")
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.call("c2v_softmax_rows", _p(x), _p(out), x.shape[0], x.shape[1], float(scale), _stream())
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma, beta, add: Optional[torch.Tensor] = None, eps: float = 1e-5, want_f32: bool = False):
     """Returns LN(x) in bf16; with `add` also LN(x)+add (bf16); with want_f32 also the un-rounded fp32 LN(x) (last)."""
     _chk(x, F32, "layernorm.x")

@@ -93,6 +93,10 @@ int c2v_groupnorm_silu(const float* x, const float* gamma, const float* beta, vo
                        int ns, int rows, int C, float eps, int silu, void* stream);
 int64_t c2v_groupnorm_ws_floats(int ns, int rows, int C);
 
+/* Row softmax: out[r, :] = softmax(scale * x[r, :]), fp32 [rows, n] -> 16-bit operands [rows, n] (n % 4 == 0).  The softmax of the
+ * single-head 512-wide attention block of the VAE decoder (ae_modules.py:53-80), whose scores / P.V products go through c2v_gemm. */
+int c2v_softmax_rows(const float* x, void* out_bf16, int rows, int n, float scale, void* stream);
+
 /* LayerNorm over the last dim (nn.LayerNorm, attention.py:232-234), fp32 in -> bf16 out.  If `add` is not
  * NULL a second output out2 = LN(x) + add is produced (normed_x + pluker features,
  * R/model/modules/modified_forwards.py:508-520); add is fp32 [rows, C].  out_f32 (optional) receives the

@@ -308,6 +308,38 @@ def gen_resampler(check):
         print(f"    oracle vs reference: rel-L2 {rel_err(yo, y)[0]:.3e}")
 
 
+def gen_vae(check):
+    """Decoder half of the first-stage AutoencoderKL (SURVEY f-3), reduced width: ch 64, two 8x8 latent frames -> 64x64 images."""
+    import json
+    rh.setup_reference_imports()
+    from lvdm.modules.networks.ae_modules import Decoder
+    dd = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
+              attn_resolutions=[], dropout=0.0)
+    torch.manual_seed(0)
+
+    class Ref(torch.nn.Module):                               # AutoencoderKL.decode (autoencoder.py:103-106) without the encoder / loss
+        def __init__(self):
+            super().__init__()
+            self.decoder = Decoder(**dd)
+            self.post_quant_conv = torch.nn.Conv2d(4, dd["z_channels"], 1)
+
+        def forward(self, z):
+            return self.decoder(self.post_quant_conv(z))
+
+    ref = Ref().eval()
+    synth.fill_module_(ref, seed=7)
+    z = synth.synth_tensor("vae.z", (2, 4, 8, 8), 11)
+    with torch.no_grad():
+        y = ref(z)
+    print(f"  vae decoder: out {tuple(y.shape)} std {y.std():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "vae_small.npz"), y=y.numpy(), ddconfig=json.dumps(dd))
+    json.dump({k: list(v.shape) for k, v in ref.state_dict().items()}, open(os.path.join(GOLD, "state_dict_vae_decoder.json"), "w"), indent=0)
+    if check:
+        from oracle import vae_oracle
+        yo = vae_oracle.decode(ref.state_dict(), z, dd["ch_mult"], dd["num_res_blocks"])
+        print(f"    oracle vs reference: rel-L2 {rel_err(yo, y)[0]:.3e}")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -330,6 +362,9 @@ if __name__ == "__main__":
     if a.only in (None, "resampler"):
         print("[resampler]")
         gen_resampler(a.check_oracle)
+    if a.only in (None, "vae"):
+        print("[vae]")
+        gen_vae(a.check_oracle)
     if a.only in ("unet_full",):
         print("[unet_full]")
         gen_unet_full(a.check_oracle)

@@ -72,3 +72,36 @@ def test_resampler_vs_reference_golden():
     l2, mx = rel(y, torch.from_numpy(g["y"]))
     print(f"resampler: rel-L2 {l2:.3e} max-norm {mx:.3e}")
     assert l2 < TOL and mx < 2 * TOL, (l2, mx)
+
+
+def test_vae_decoder_vs_reference_golden():
+    """decode_first_stage (SURVEY f-3): AutoencoderKL.decode / ae_modules.Decoder against the unmodified reference classes."""
+    from camc2v_b200 import synth
+    from camc2v_b200.vae import AutoencoderKLDecoder
+    g = np.load(os.path.join(GOLD, "vae_small.npz"))
+    dd = json.loads(str(g["ddconfig"]))
+    m = AutoencoderKLDecoder(dd)
+    synth.fill_module_(m, seed=7)
+    m = m.to(DEV)
+    z = synth.synth_tensor("vae.z", (2, 4, 8, 8), 11).to(DEV)
+    y = m.decode(z)
+    assert y.shape == (2, 3, 64, 64) and torch.isfinite(y).all()
+    l2, mx = rel(y, torch.from_numpy(g["y"]))
+    print(f"vae decoder: rel-L2 {l2:.3e} max-norm {mx:.3e}")
+    assert l2 < TOL and mx < 2 * TOL, (l2, mx)
+
+
+def test_conv3x3_on_images_wider_than_a_tile():
+    """256-pixel rows (the VAE decoder's last level): one 128-pixel tile is half an image row; TMA zero fill is the padding."""
+    from camc2v_b200 import ops
+    NB, H, W, Cin, Cout = 2, 8, 256, 64, 128
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(NB, Cin, H, W, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen) * (9 * Cin) ** -0.5
+    b = torch.randn(Cout, generator=gen)
+    xb, wb = x.to(ops.BF16), w.to(ops.BF16)
+    ref = torch.nn.functional.conv2d(xb.float(), wb.float(), b, padding=1).permute(0, 2, 3, 1).reshape(NB * H * W, Cout)
+    a = xb.permute(0, 2, 3, 1).reshape(NB * H * W, Cin).contiguous().to(DEV)
+    wk = wb.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().to(DEV)
+    out = ops.conv3x3(a, wk, NB, H, W, bias=b.to(DEV))
+    assert (out.cpu() - ref).abs().max() <= 2e-3 * ref.abs().max()

@@ -236,3 +236,20 @@ def test_resampler_oracle_matches_reference():
     y = resampler_oracle.resampler_forward(sd, x, depth=kw["depth"], heads=kw["heads"])
     l2, mx = _rel(y, torch.from_numpy(g["y"]))
     assert l2 < 1e-5 and mx < 1e-5, (l2, mx)
+
+
+# ------------------------------------------------------------------------------------------------ VAE decoder (SURVEY f-3)
+def test_vae_decoder_oracle_matches_reference():
+    import json
+    from camc2v_b200.vae import AutoencoderKLDecoder
+    from oracle import vae_oracle
+    g = np.load(os.path.join(GOLD, "vae_small.npz"))
+    dd = json.loads(str(g["ddconfig"]))
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in AutoencoderKLDecoder(dd).state_dict().items()}
+    assert {k: list(v) for k, v in shapes.items()} == json.load(open(os.path.join(GOLD, "state_dict_vae_decoder.json")))   # drop-in state_dict
+    sd = synth.synth_state_dict(shapes, 7)
+    z = synth.synth_tensor("vae.z", (2, 4, 8, 8), 11)
+    y = vae_oracle.decode(sd, z, dd["ch_mult"], dd["num_res_blocks"])
+    l2, mx = _rel(y, torch.from_numpy(g["y"]))
+    assert l2 < 1e-5 and mx < 1e-5, (l2, mx)
