@@ -103,8 +103,51 @@ def resampler_main():
     print(json.dumps(line))
 
 
+def vae_main():
+    """decode_first_stage at the shipped size (camcontexti2v_256.yaml:74-93): 16 latent frames [4, 32, 32] -> 16 x [3, 256, 256]."""
+    from camc2v_b200.vae import AutoencoderKLDecoder
+    dev = torch.device("cuda", 0)
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
+              attn_resolutions=[], dropout=0.0)
+    m = AutoencoderKLDecoder(dd)
+    synth.fill_module_(m, seed=7)
+    m = m.to(dev)
+    z = synth.synth_tensor("vae.z", (16, 4, 32, 32), 11).to(dev)
+    for _ in range(2):
+        y = m.decode(z)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        y = m.decode(z)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    # conv FLOPs per frame (2 * HW * 9 * Cin * Cout), the dominant term
+    def conv(hw, ci, co, k=9):
+        return 2.0 * hw * k * ci * co
+    fl = conv(1024, 4, 512) + 2 * 2 * conv(1024, 512, 512) + 3 * 2 * conv(1024, 512, 512) + conv(4096, 512, 512) + 3 * 2 * conv(4096, 512, 512) + \
+        conv(16384, 512, 512) + conv(16384, 512, 256) + 5 * conv(16384, 256, 256) + conv(65536, 256, 256) + conv(65536, 256, 128) + \
+        5 * conv(65536, 128, 128) + conv(65536, 128, 3) + 4 * 2.0 * 1024 * 512 * 512 + 2 * 2.0 * 1024 * 1024 * 512
+    line = {"metric": "vae_decode_ms_per_video", "value": ms, "unit": "ms (AutoencoderKL.decode, 16 frames 32x32 latent -> 256x256 RGB)",
+            "algorithmic_tflop": 16 * fl / 1e12, "tflops": 16 * fl / ms / 1e9, "finite": bool(torch.isfinite(y).all()), "dtype": ops._lib.OPERANDS}
+    if "--no-cpu" not in sys.argv:
+        from oracle import vae_oracle
+        sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+        t0 = time.perf_counter()
+        yo = vae_oracle.decode(sd, z[:1].cpu(), dd["ch_mult"], dd["num_res_blocks"])
+        s1 = time.perf_counter() - t0
+        a, b = y[:1].cpu().double(), yo.double()
+        line["cpu_baseline"] = {"value": s1 * 16 * 1e3, "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"oracle (CPU port of the reference, fp32) on 1 of the 16 frames: {s1:.2f} s, scaled x16"}
+        line["parity_full_size_frame0"] = {"rel_l2": float((a - b).norm() / b.norm()), "max_norm": float((a - b).abs().max() / b.abs().max())}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
-    if "--resampler" in sys.argv:
+    if "--vae" in sys.argv:
+        vae_main()
+    elif "--resampler" in sys.argv:
         resampler_main()
     else:
         main()
