@@ -375,7 +375,12 @@ int c2v_upsample2x(const float* in, void* out, int N, int H, int W, int C, void*
 
 int c2v_im2col_s2(const float* in, void* out, int N, int H, int W, int C, void* stream) {
     if (!in || !out) return ERR_BAD_ARG;
-    return im2col_s2_launch(in, out, N, H, W, C, (cudaStream_t)stream);
+    return im2col_s2_launch(in, out, N, H, W, C, 1, (cudaStream_t)stream);
+}
+
+int c2v_im2col_s2_pad(const float* in, void* out, int N, int H, int W, int C, int pad_lo, void* stream) {
+    if (!in || !out || (pad_lo != 0 && pad_lo != 1)) return ERR_BAD_ARG;
+    return im2col_s2_launch(in, out, N, H, W, C, pad_lo, (cudaStream_t)stream);
 }
 
 int c2v_copy_rows(const void* src, void* dst, int rows, int C, int B, int64_t dst_bstride, int ldd, void* stream) {

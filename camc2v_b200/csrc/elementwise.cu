@@ -132,7 +132,9 @@ int upsample2x_launch(const float* in, void* out, int N, int H, int W, int C, cu
 }
 
 // im2col of the stride-2 Downsample conv (openaimodel3d.py:66-70): row (n, yo, xo), column tap*C + c
-__global__ void im2col_s2_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+// pad_lo = 1: symmetric padding 1 (UNet Downsample, openaimodel3d.py:68-70); pad_lo = 0: zero padding on the right / bottom only
+// (VAE encoder Downsample, ae_modules.py:102-106)
+__global__ void im2col_s2_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C, int pad_lo) {
     const int nv = C >> 2, Ho = H >> 1, Wo = W >> 1;
     const int64_t total = (int64_t)N * Ho * Wo * 9 * nv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -142,16 +144,16 @@ __global__ void im2col_s2_kernel(const float* __restrict__ in, __nv_bfloat16* __
         const int xo = (int)(r % Wo); r /= Wo;
         const int yo = (int)(r % Ho);
         const int n = (int)(r / Ho);
-        const int y = 2 * yo + tap / 3 - 1, x = 2 * xo + tap % 3 - 1;
+        const int y = 2 * yo + tap / 3 - pad_lo, x = 2 * xo + tap % 3 - pad_lo;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < H && x >= 0 && x < W) v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + y) * W + x) * C + cv * 4);
         *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     }
 }
 
-int im2col_s2_launch(const float* in, void* out, int N, int H, int W, int C, cudaStream_t st) {
+int im2col_s2_launch(const float* in, void* out, int N, int H, int W, int C, int pad_lo, cudaStream_t st) {
     if (C % 4 || H % 2 || W % 2) return ERR_UNSUPPORTED;
-    im2col_s2_kernel<<<grid_for((int64_t)N * (H / 2) * (W / 2) * 9 * (C >> 2), 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), N, H, W, C);
+    im2col_s2_kernel<<<grid_for((int64_t)N * (H / 2) * (W / 2) * 9 * (C >> 2), 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), N, H, W, C, pad_lo);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -20,7 +20,7 @@ int from_channels_last_launch(const float* in, float* out, int B, int C, int S, 
 int concat_channels_launch(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, cudaStream_t st);
 int cast_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t st);
 int upsample2x_launch(const float* in, void* out, int N, int H, int W, int C, cudaStream_t st);
-int im2col_s2_launch(const float* in, void* out, int N, int H, int W, int C, cudaStream_t st);
+int im2col_s2_launch(const float* in, void* out, int N, int H, int W, int C, int pad_lo, cudaStream_t st);
 int copy_rows_launch(const void* src, void* dst, int rows, int C, int B, int64_t dst_bstride, int ldd, cudaStream_t st);
 int skinny_linear_launch(const float* in, const void* w, const float* bias, float* out, int M, int N, int K, int silu_in, cudaStream_t st);
 int timestep_embedding_launch(const int64_t* t, float* out, int n, int dim, cudaStream_t st);

@@ -310,10 +310,12 @@ def upsample2x(x: torch.Tensor, N: int, H: int, W: int):
     return out
 
 
-def im2col_s2(x: torch.Tensor, N: int, H: int, W: int):
+def im2col_s2(x: torch.Tensor, N: int, H: int, W: int, pad_lo: int = 1):
+    """Patches of a stride-2 3x3 conv: pad_lo = 1 symmetric padding 1 (UNet Downsample), pad_lo = 0 right / bottom padding only
+    (VAE encoder Downsample)."""
     C_ = x.shape[1]
     out = torch.empty((N * (H // 2) * (W // 2), 9 * C_), device=x.device, dtype=BF16)
-    _lib.call("c2v_im2col_s2", _p(x), _p(out), N, H, W, C_, _stream())
+    _lib.call("c2v_im2col_s2_pad", _p(x), _p(out), N, H, W, C_, pad_lo, _stream())
     return out
 
 

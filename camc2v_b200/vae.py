@@ -122,6 +122,100 @@ class Decoder(_Prepared):
         self.conv_out = nn.Conv2d(block_in, out_ch, 3, 1, 1)
 
 
+class Downsample(nn.Module):
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        assert with_conv
+        self.conv = nn.Conv2d(in_channels, in_channels, 3, 2, 0)
+
+
+class Encoder(nn.Module):
+    """Parameter holder of ae_modules.py:364-428."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0, resamp_with_conv=True, in_channels,
+                 resolution, z_channels, double_z=True, use_linear_attn=False, attn_type="vanilla", **ignore_kwargs):
+        super().__init__()
+        if list(attn_resolutions) or use_linear_attn or attn_type != "vanilla":
+            raise NotImplementedError("encoder options the shipped first_stage_config leaves off")
+        self.ch_mult, self.num_res_blocks, self.in_channels = tuple(ch_mult), num_res_blocks, in_channels
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, 1, 1)
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for lvl in range(len(ch_mult)):
+            block = nn.ModuleList()
+            block_in, block_out = ch * in_ch_mult[lvl], ch * ch_mult[lvl]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out))
+                block_in = block_out
+            down = nn.Module()
+            down.block, down.attn = block, nn.ModuleList()
+            if lvl != len(ch_mult) - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, 3, 1, 1)
+
+
+class AutoencoderKLEncoder(_Prepared):
+    """`encoder` + `quant_conv` of lvdm.models.autoencoder.AutoencoderKL (autoencoder.py:97-101), state_dict-compatible.
+    `encode` returns the posterior moments [mean | logvar]; sampling the DiagonalGaussianDistribution stays with the caller."""
+
+    def __init__(self, ddconfig: dict, embed_dim: int = 4):
+        super().__init__()
+        assert ddconfig.get("double_z", True)
+        self.encoder = Encoder(**ddconfig)
+        self.quant_conv = nn.Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
+
+    def _prepare(self):
+        e = self.encoder
+        w_in, b_in = _conv3x3_pack(e.conv_in, pad_cin=64)
+        # quant_conv (1x1) follows conv_out (3x3) with nothing in between: W_q (W_out * x + b_out) + b_q is one 3x3 conv (exact fold)
+        wq = self.quant_conv.weight.detach().float().reshape(self.quant_conv.out_channels, -1)
+        wo = e.conv_out.weight.detach().float()
+        w_f = torch.einsum("om,mikl->oikl", wq, wo)
+        b_f = wq @ e.conv_out.bias.detach().float() + self.quant_conv.bias.detach().float()
+        p = dict(w_in=w_in, b_in=b_in, mid1=e.mid.block_1.pack(), attn=e.mid.attn_1.pack(), mid2=e.mid.block_2.pack(),
+                 g_out=_f32(e.norm_out.weight), be_out=_f32(e.norm_out.bias),
+                 w_out=_bf16(w_f.permute(0, 2, 3, 1).reshape(w_f.shape[0], -1)), b_out=_f32(b_f), down=[])
+        for d in e.down:
+            u = dict(blocks=[b.pack() for b in d.block])
+            if hasattr(d, "downsample"):
+                w = d.downsample.conv.weight.detach()
+                u["w_dn"], u["b_dn"] = _bf16(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)), _f32(d.downsample.conv.bias)
+            p["down"].append(u)
+        return p
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        """x fp32 [N, 3, H, W] -> moments fp32 [N, 2*embed_dim, H/8, W/8]."""
+        p = self.pk()
+        e = self.encoder
+        N, c, H, W = x.shape
+        xin = ops.to_channels_last(_f32(x), N, c, H * W, Cpad=64, dtype=ops.BF16)
+        h = ops.conv3x3(xin, p["w_in"], N, H, W, bias=p["b_in"])
+        for lvl in range(len(e.ch_mult)):
+            u = p["down"][lvl]
+            for bp in u["blocks"]:
+                h = ResnetBlock.run(bp, h, N, H, W)
+            if "w_dn" in u:
+                cols = ops.im2col_s2(h, N, H, W, pad_lo=0)                                   # F.pad(x, (0,1,0,1)) + stride-2 conv
+                H, W = H // 2, W // 2
+                h = ops.linear(cols, u["w_dn"], bias=u["b_dn"])
+        h = ResnetBlock.run(p["mid1"], h, N, H, W)
+        h = AttnBlock.run(p["attn"], h, N, H, W)
+        h = ResnetBlock.run(p["mid2"], h, N, H, W)
+        n = ops.groupnorm(h, p["g_out"], p["be_out"], N, H * W, 1e-6, True)
+        y = ops.conv3x3(n, p["w_out"], N, H, W, bias=p["b_out"])                              # conv_out and quant_conv, folded
+        return ops.from_channels_last(y, N, y.shape[1], H * W).view(N, -1, H, W)
+
+    forward = encode
+
+
 class AutoencoderKLDecoder(_Prepared):
     """`post_quant_conv` + `decoder` of lvdm.models.autoencoder.AutoencoderKL (autoencoder.py:103-106), state_dict-compatible."""
 

@@ -183,6 +183,9 @@ int c2v_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 int c2v_upsample2x(const float* in, void* out_bf16, int N, int H, int W, int C, void* stream);
 /* im2col for the stride-2 3x3 Downsample conv (openaimodel3d.py:68-70): fp32 [N,H,W,C] -> bf16 [N*(H/2)*(W/2), 9*C]. */
 int c2v_im2col_s2(const float* in, void* out_bf16, int N, int H, int W, int C, void* stream);
+/* Same with the padding made explicit: pad_lo = 1 is c2v_im2col_s2; pad_lo = 0 pads on the right / bottom only, which is the
+ * `F.pad(x, (0,1,0,1))` + stride-2 conv of the VAE encoder's Downsample (ae_modules.py:102-106). */
+int c2v_im2col_s2_pad(const float* in, void* out_bf16, int N, int H, int W, int C, int pad_lo, void* stream);
 /* out[b, r + row_off, :] = src[r, :] for r < rows (bf16): writes the pre-projected register tokens in front of K / V. */
 int c2v_copy_rows(const void* src_bf16, void* dst_bf16, int rows, int C, int B, int64_t dst_bstride, int ldd, void* stream);
 

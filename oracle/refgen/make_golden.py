@@ -339,6 +339,31 @@ def gen_vae(check):
         yo = vae_oracle.decode(ref.state_dict(), z, dd["ch_mult"], dd["num_res_blocks"])
         print(f"    oracle vs reference: rel-L2 {rel_err(yo, y)[0]:.3e}")
 
+    # encoder half: AutoencoderKL.encode (autoencoder.py:97-101) up to the posterior moments
+    from lvdm.modules.networks.ae_modules import Encoder
+
+    class RefE(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = Encoder(**dd)
+            self.quant_conv = torch.nn.Conv2d(2 * dd["z_channels"], 2 * 4, 1)
+
+        def forward(self, x):
+            return self.quant_conv(self.encoder(x))
+
+    torch.manual_seed(0)
+    refe = RefE().eval()
+    synth.fill_module_(refe, seed=8)
+    x = synth.synth_tensor("vae.x", (2, 3, 64, 64), 12)
+    with torch.no_grad():
+        mom = refe(x)
+    print(f"  vae encoder: moments {tuple(mom.shape)} std {mom.std():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "vae_enc_small.npz"), moments=mom.numpy(), ddconfig=json.dumps(dd))
+    json.dump({k: list(v.shape) for k, v in refe.state_dict().items()}, open(os.path.join(GOLD, "state_dict_vae_encoder.json"), "w"), indent=0)
+    if check:
+        mo = vae_oracle.encode_moments(refe.state_dict(), x, dd["ch_mult"], dd["num_res_blocks"])
+        print(f"    encoder oracle vs reference: rel-L2 {rel_err(mo, mom)[0]:.3e}")
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -1,8 +1,8 @@
 """CPU ORACLE (test infrastructure, NOT product code): decoder half of the first-stage AutoencoderKL.
 
 fp32 functional restatement, driven by a reference-format state_dict (keys `post_quant_conv.*`, `decoder.*`), of
-  * AutoencoderKL.decode          R/lvdm/models/autoencoder.py:103-106
-  * Decoder.forward               R/lvdm/modules/networks/ae_modules.py:471-583
+  * AutoencoderKL.decode / encode R/lvdm/models/autoencoder.py:97-106 (encode returns the moments [mean | logvar] of the posterior)
+  * Decoder.forward               R/lvdm/modules/networks/ae_modules.py:471-583;  Encoder.forward :364-468, Downsample :90-108
   * ResnetBlock / AttnBlock / Upsample / Normalize   ae_modules.py:151-209, 26-80, 111-126, 16-17 (GroupNorm 32, eps 1e-6; swish)
 Pinned by tests/golden/vae_small.npz (output of the unmodified reference classes, oracle/refgen/make_golden.py)."""
 from __future__ import annotations
@@ -51,3 +51,19 @@ def decode(sd: Dict[str, torch.Tensor], z: torch.Tensor, ch_mult: Sequence[int] 
         if lvl != 0:
             h = _conv(sd, f"decoder.up.{lvl}.upsample.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"), 1)
     return _conv(sd, "decoder.conv_out", F.silu(_gn(sd, "decoder.norm_out", h)), 1)
+
+
+def encode_moments(sd: Dict[str, torch.Tensor], x: torch.Tensor, ch_mult: Sequence[int] = (1, 2, 4, 4), num_res_blocks: int = 2) -> torch.Tensor:
+    """x [N, 3, H, W] -> moments [N, 2*z_channels, H/8, W/8] = quant_conv(encoder(x)) (mean = first half, logvar = second half)."""
+    h = _conv(sd, "encoder.conv_in", x, 1)
+    for lvl in range(len(ch_mult)):
+        for i in range(num_res_blocks):
+            h = _res(sd, f"encoder.down.{lvl}.block.{i}", h)
+        if lvl != len(ch_mult) - 1:
+            n = f"encoder.down.{lvl}.downsample.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[n + ".weight"], sd[n + ".bias"], stride=2)
+    h = _res(sd, "encoder.mid.block_1", h)
+    h = _attn(sd, "encoder.mid.attn_1", h)
+    h = _res(sd, "encoder.mid.block_2", h)
+    h = _conv(sd, "encoder.conv_out", F.silu(_gn(sd, "encoder.norm_out", h)), 1)
+    return _conv(sd, "quant_conv", h, 0)

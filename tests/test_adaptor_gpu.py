@@ -105,3 +105,20 @@ def test_conv3x3_on_images_wider_than_a_tile():
     wk = wb.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().to(DEV)
     out = ops.conv3x3(a, wk, NB, H, W, bias=b.to(DEV))
     assert (out.cpu() - ref).abs().max() <= 2e-3 * ref.abs().max()
+
+
+def test_vae_encoder_vs_reference_golden():
+    """encode_first_stage up to the posterior moments (SURVEY f-3): ae_modules.Encoder + quant_conv against the reference classes."""
+    from camc2v_b200 import synth
+    from camc2v_b200.vae import AutoencoderKLEncoder
+    g = np.load(os.path.join(GOLD, "vae_enc_small.npz"))
+    dd = json.loads(str(g["ddconfig"]))
+    m = AutoencoderKLEncoder(dd)
+    synth.fill_module_(m, seed=8)
+    m = m.to(DEV)
+    x = synth.synth_tensor("vae.x", (2, 3, 64, 64), 12).to(DEV)
+    mom = m.encode(x)
+    assert mom.shape == (2, 8, 8, 8) and torch.isfinite(mom).all()
+    l2, mx = rel(mom, torch.from_numpy(g["moments"]))
+    print(f"vae encoder: rel-L2 {l2:.3e} max-norm {mx:.3e}")
+    assert l2 < TOL and mx < 2 * TOL, (l2, mx)

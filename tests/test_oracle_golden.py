@@ -253,3 +253,19 @@ def test_vae_decoder_oracle_matches_reference():
     y = vae_oracle.decode(sd, z, dd["ch_mult"], dd["num_res_blocks"])
     l2, mx = _rel(y, torch.from_numpy(g["y"]))
     assert l2 < 1e-5 and mx < 1e-5, (l2, mx)
+
+
+def test_vae_encoder_oracle_matches_reference():
+    import json
+    from camc2v_b200.vae import AutoencoderKLEncoder
+    from oracle import vae_oracle
+    g = np.load(os.path.join(GOLD, "vae_enc_small.npz"))
+    dd = json.loads(str(g["ddconfig"]))
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in AutoencoderKLEncoder(dd).state_dict().items()}
+    assert {k: list(v) for k, v in shapes.items()} == json.load(open(os.path.join(GOLD, "state_dict_vae_encoder.json")))   # drop-in state_dict
+    sd = synth.synth_state_dict(shapes, 8)
+    x = synth.synth_tensor("vae.x", (2, 3, 64, 64), 12)
+    mom = vae_oracle.encode_moments(sd, x, dd["ch_mult"], dd["num_res_blocks"])
+    l2, mx = _rel(mom, torch.from_numpy(g["moments"]))
+    assert l2 < 1e-5 and mx < 1e-5, (l2, mx)
