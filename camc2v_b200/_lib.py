@@ -86,6 +86,7 @@ PROTOTYPES = {
     "c2v_im2col_s2_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_copy_rows": (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _vp]),
     "c2v_cfg_ddim_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _f, _f, _vp]),
+    "c2v_cfg_ddim_update_cam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _f, _f, _f, _vp]),
 }
 
 _lib = None

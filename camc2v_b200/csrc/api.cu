@@ -392,8 +392,16 @@ int c2v_cfg_ddim_update(const float* x, const float* e_cond, const float* e_unco
                         int64_t n, float scale, float guidance_rescale, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
                         void* stream) {
     if (!x || !e_cond || !e_uncond || !noise || !x_prev || !pred_x0) return ERR_BAD_ARG;
-    return cfg_ddim_update_launch(x, e_cond, e_uncond, noise, x_prev, pred_x0, B, n, scale, guidance_rescale, a_t, a_prev, sigma_t,
+    return cfg_ddim_update_launch(x, e_cond, e_uncond, nullptr, noise, x_prev, pred_x0, B, n, scale, 0.f, guidance_rescale, a_t, a_prev, sigma_t,
                                   sqrt_one_minus_at, (cudaStream_t)stream);
+}
+
+int c2v_cfg_ddim_update_cam(const float* x, const float* e_cond, const float* e_uncond, const float* e_cond_nocam, const float* noise,
+                            float* x_prev, float* pred_x0, int B, int64_t n, float scale, float cam_weight, float guidance_rescale, float a_t,
+                            float a_prev, float sigma_t, float sqrt_one_minus_at, void* stream) {
+    if (!x || !e_cond || !e_uncond || !e_cond_nocam || !noise || !x_prev || !pred_x0) return ERR_BAD_ARG;
+    return cfg_ddim_update_launch(x, e_cond, e_uncond, e_cond_nocam, noise, x_prev, pred_x0, B, n, scale, cam_weight, guidance_rescale, a_t, a_prev,
+                                  sigma_t, sqrt_one_minus_at, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -291,27 +291,36 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return sh[0];
 }
 
+// model_output = e_u + scale (e_c - e_u) [+ cam_w (e_c - e_nc)]: the optional third term is the reference's camera guidance
+// (ddim.py:268-280; e_nc = the conditional pass WITHOUT the camera condition, cam_w = (camera_cfg - 1) * scheduler weight)
+__device__ __forceinline__ float cfg_combine(float c, float u, float scale, const float* __restrict__ enc, int64_t i, float cam_w) {
+    float e = __fadd_rn(u, __fmul_rn(scale, __fsub_rn(c, u)));
+    if (enc) e = __fadd_rn(e, __fmul_rn(cam_w, __fsub_rn(c, enc[i])));
+    return e;
+}
+
 __global__ void __launch_bounds__(1024) cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ ec, const float* __restrict__ eu,
-                                                        const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0,
-                                                        int64_t n, float scale, float phi, float a_t, float a_prev, float sigma_t,
-                                                        float sqrt_one_minus_at) {
+                                                        const float* __restrict__ enc, const float* __restrict__ noise, float* __restrict__ x_prev,
+                                                        float* __restrict__ pred_x0, int64_t n, float scale, float cam_w, float phi, float a_t,
+                                                        float a_prev, float sigma_t, float sqrt_one_minus_at) {
     __shared__ double sh[32];
     const size_t base = (size_t)blockIdx.x * n;
     x += base; ec += base; eu += base; noise += base; x_prev += base; pred_x0 += base;
+    if (enc) enc += base;
     float ratio = 1.f;
     if (phi > 0.f) {
         double sc = 0.0, se = 0.0;
         for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
             const float c = ec[i], u = eu[i];
             sc += c;
-            se += __fadd_rn(u, __fmul_rn(scale, __fsub_rn(c, u)));
+            se += cfg_combine(c, u, scale, enc, i, cam_w);
         }
         const double mc = block_sum(sc, sh) / (double)n;
         const double me = block_sum(se, sh) / (double)n;
         double vc = 0.0, ve = 0.0;
         for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
             const float c = ec[i], u = eu[i];
-            const float e = __fadd_rn(u, __fmul_rn(scale, __fsub_rn(c, u)));
+            const float e = cfg_combine(c, u, scale, enc, i, cam_w);
             vc += ((double)c - mc) * ((double)c - mc);
             ve += ((double)e - me) * ((double)e - me);
         }
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(1024) cfg_ddim_kernel(const float* __restrict_
     const float dir = sqrtf(fmaxf(1.0f - a_prev - sigma_t * sigma_t, 0.f));
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
         const float c = ec[i], u = eu[i];
-        float e = __fadd_rn(u, __fmul_rn(scale, __fsub_rn(c, u)));
+        float e = cfg_combine(c, u, scale, enc, i, cam_w);
         if (phi > 0.f) e = __fadd_rn(__fmul_rn(phi, __fmul_rn(e, ratio)), __fmul_rn(1.0f - phi, e));
         const float p0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
         pred_x0[i] = p0;
@@ -331,11 +340,11 @@ __global__ void __launch_bounds__(1024) cfg_ddim_kernel(const float* __restrict_
     }
 }
 
-int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, const float* noise, float* x_prev, float* pred_x0, int B,
-                           int64_t n, float scale, float phi, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
-                           cudaStream_t st) {
+int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, const float* enc, const float* noise, float* x_prev,
+                           float* pred_x0, int B, int64_t n, float scale, float cam_w, float phi, float a_t, float a_prev, float sigma_t,
+                           float sqrt_one_minus_at, cudaStream_t st) {
     if (B <= 0 || n <= 1) return ERR_BAD_ARG;
-    cfg_ddim_kernel<<<B, 1024, 0, st>>>(x, ec, eu, noise, x_prev, pred_x0, n, scale, phi, a_t, a_prev, sigma_t, sqrt_one_minus_at);
+    cfg_ddim_kernel<<<B, 1024, 0, st>>>(x, ec, eu, enc, noise, x_prev, pred_x0, n, scale, cam_w, phi, a_t, a_prev, sigma_t, sqrt_one_minus_at);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -24,9 +24,9 @@ int im2col_s2_launch(const float* in, void* out, int N, int H, int W, int C, int
 int copy_rows_launch(const void* src, void* dst, int rows, int C, int B, int64_t dst_bstride, int ldd, cudaStream_t st);
 int skinny_linear_launch(const float* in, const void* w, const float* bias, float* out, int M, int N, int K, int silu_in, cudaStream_t st);
 int timestep_embedding_launch(const int64_t* t, float* out, int n, int dim, cudaStream_t st);
-int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, const float* noise, float* x_prev, float* pred_x0, int B,
-                           int64_t n, float scale, float phi, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
-                           cudaStream_t st);
+int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, const float* enc, const float* noise, float* x_prev,
+                           float* pred_x0, int B, int64_t n, float scale, float cam_w, float phi, float a_t, float a_prev, float sigma_t,
+                           float sqrt_one_minus_at, cudaStream_t st);
 
 // attn_t16.cu
 int attention_temporal_launch(const void* qkv, void* out, int B, int T, int HW, int heads, cudaStream_t st);

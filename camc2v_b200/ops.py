@@ -319,15 +319,22 @@ def im2col_s2(x: torch.Tensor, N: int, H: int, W: int, pad_lo: int = 1):
     return out
 
 
-def cfg_ddim_update(x, e_cond, e_uncond, noise, scale, guidance_rescale, a_t, a_prev, sigma_t, sqrt_one_minus_at):
-    """Fused CFG combine + guidance rescale + DDIM update (ddim.py:262-346).  Returns (x_prev, pred_x0)."""
-    for t in (x, e_cond, e_uncond, noise):
+def cfg_ddim_update(x, e_cond, e_uncond, noise, scale, guidance_rescale, a_t, a_prev, sigma_t, sqrt_one_minus_at, e_cond_nocam=None,
+                    cam_weight: float = 0.0):
+    """Fused CFG combine (+ optional camera guidance term, ddim.py:268-280) + guidance rescale + DDIM update (ddim.py:262-346).
+    Returns (x_prev, pred_x0)."""
+    for t in (x, e_cond, e_uncond, noise) + ((e_cond_nocam,) if e_cond_nocam is not None else ()):
         _chk(t, F32, "cfg_ddim_update")
     B = x.shape[0]
     n = x.numel() // B
     x_prev = torch.empty_like(x)
     pred_x0 = torch.empty_like(x)
-    _lib.call("c2v_cfg_ddim_update", _p(x.contiguous()), _p(e_cond.contiguous()), _p(e_uncond.contiguous()), _p(noise.contiguous()),
-              _p(x_prev), _p(pred_x0), B, n, float(scale), float(guidance_rescale), float(a_t), float(a_prev), float(sigma_t),
-              float(sqrt_one_minus_at), _stream())
+    if e_cond_nocam is None:
+        _lib.call("c2v_cfg_ddim_update", _p(x.contiguous()), _p(e_cond.contiguous()), _p(e_uncond.contiguous()), _p(noise.contiguous()),
+                  _p(x_prev), _p(pred_x0), B, n, float(scale), float(guidance_rescale), float(a_t), float(a_prev), float(sigma_t),
+                  float(sqrt_one_minus_at), _stream())
+    else:
+        _lib.call("c2v_cfg_ddim_update_cam", _p(x.contiguous()), _p(e_cond.contiguous()), _p(e_uncond.contiguous()), _p(e_cond_nocam.contiguous()),
+                  _p(noise.contiguous()), _p(x_prev), _p(pred_x0), B, n, float(scale), float(cam_weight), float(guidance_rescale), float(a_t),
+                  float(a_prev), float(sigma_t), float(sqrt_one_minus_at), _stream())
     return x_prev, pred_x0

@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -92,6 +94,7 @@ class DDIMSampler(object):
         self._graph = None
         self.concurrent_passes = kwargs.get("concurrent_passes", True)
         self.cfg_pair = kwargs.get("cfg_pair", None)       # parallel.CfgPair: split the CFG halves over two ranks
+        self._derived = {}                                  # conditioning dicts derived from the caller's (stable identity for the graph key)
 
     # -------------------------------------------------------------------------------------------- schedule
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
@@ -210,9 +213,10 @@ class DDIMSampler(object):
         a_prev = float(self.ddim_alphas_prev[index])
         sigma_t = float(self.ddim_sigmas[index])
         s1m = float(self.ddim_sqrt_one_minus_alphas[index])
-        camera_cfg = kwargs.get("camera_cfg", 1.0)
-        if camera_cfg != 1.0:
-            raise NotImplementedError("camera_cfg != 1.0 (third UNet pass, ddim.py:268-280)")
+        camera_cfg = float(kwargs.pop("camera_cfg", 1.0))
+        camera_cfg_scheduler = kwargs.pop("camera_cfg_scheduler", "constant")
+        if camera_cfg_scheduler not in ("constant", "cosine"):
+            raise NotImplementedError(camera_cfg_scheduler)
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
             e_c = self.model.apply_model(x, t, c, **kwargs)
             e_u, scale, phi = e_c, 1.0, 0.0
@@ -223,7 +227,21 @@ class DDIMSampler(object):
                 cam = c.get("camera_condition")
                 if cam is not None and uc.get("camera_condition") is not cam:
                     uc["camera_condition"] = cam
-            if self.cfg_pair is not None:
+            e_nc, cam_w = None, 0.0
+            if camera_cfg != 1.0 and kwargs.get("enable_camera_condition", False) and isinstance(c, dict):
+                # camera guidance (ddim.py:268-280): a third pass, conditional but without the camera condition
+                if self.cfg_pair is not None:
+                    raise NotImplementedError("camera_cfg != 1 together with CFG-split")
+                key = ("nocam", id(c))
+                c_nc = self._derived.get(key)
+                if c_nc is None:
+                    self._derived.clear()
+                    c_nc = self._derived[key] = {k: v for k, v in c.items() if k != "camera_condition"}
+                e_c, e_u, e_nc = self._unet_passes(x, t, [c, uc, c_nc], kwargs, use_cuda_graph)
+                # scheduler weight from the HOST copy of the timestep (ddim_timesteps[index] == t): no device sync
+                w = 1.0 if camera_cfg_scheduler == "constant" else math.cos((1.0 - float(self.ddim_timesteps[index]) / 999.0) * math.pi / 2.0)
+                cam_w = (camera_cfg - 1.0) * w
+            elif self.cfg_pair is not None:
                 # CFG-split (parallel.CfgPair): this rank runs ONE of the two passes, the pair exchanges the predictions
                 e_loc = self._unet_passes(x, t, [c if self.cfg_pair.role == 0 else uc], kwargs, use_cuda_graph)[0]
                 e_c, e_u = self.cfg_pair.exchange(e_loc)
@@ -236,4 +254,4 @@ class DDIMSampler(object):
             noise = torch.randn(x.shape, device=x.device)
         if temperature != 1.:
             noise = noise * temperature
-        return ops.cfg_ddim_update(x.float(), e_c, e_u, noise, scale, phi, a_t, a_prev, sigma_t, s1m)
+        return ops.cfg_ddim_update(x.float(), e_c, e_u, noise, scale, phi, a_t, a_prev, sigma_t, s1m, e_cond_nocam=e_nc, cam_weight=cam_w)

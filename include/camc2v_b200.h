@@ -199,6 +199,12 @@ int c2v_copy_rows(const void* src_bf16, void* dst_bf16, int rows, int C, int B, 
 int c2v_cfg_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise, float* x_prev, float* pred_x0,
                         int B, int64_t n, float scale, float guidance_rescale, float a_t, float a_prev, float sigma_t,
                         float sqrt_one_minus_at, void* stream);
+/* The same with the reference's camera guidance (ddim.py:268-280, `camera_cfg != 1`): a third UNet pass e_cond_nocam (the
+ * conditional pass without the camera condition) enters as  model_output += cam_weight * (e_cond - e_cond_nocam)  before the
+ * guidance rescale; cam_weight = (camera_cfg - 1) * scheduler weight (1 for "constant", cos((1 - t/999) pi/2) for "cosine"). */
+int c2v_cfg_ddim_update_cam(const float* x, const float* e_cond, const float* e_uncond, const float* e_cond_nocam, const float* noise,
+                            float* x_prev, float* pred_x0, int B, int64_t n, float scale, float cam_weight, float guidance_rescale, float a_t,
+                            float a_prev, float sigma_t, float sqrt_one_minus_at, void* stream);
 
 #ifdef __cplusplus
 }

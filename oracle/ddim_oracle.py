@@ -42,10 +42,14 @@ def ddim_schedule(n_ddim=25, eta=1.0, method="uniform_trailing", n_ddpm=1000):
                 sigmas=sig.astype(np.float32), sqrt_one_minus_alphas=np.sqrt(1.0 - a).astype(np.float32))
 
 
-def cfg_ddim_update(x, e_cond, e_uncond, noise, a_t, a_prev, sigma_t, sqrt_one_minus_at, scale, guidance_rescale):
-    """All tensors [B,C,T,H,W] fp32; scalars are python floats (fp32 values).  Returns (x_prev, pred_x0)."""
+def cfg_ddim_update(x, e_cond, e_uncond, noise, a_t, a_prev, sigma_t, sqrt_one_minus_at, scale, guidance_rescale, e_cond_nocam=None,
+                    cam_weight=0.0):
+    """All tensors [B,C,T,H,W] fp32; scalars are python floats (fp32 values).  Returns (x_prev, pred_x0).
+    e_cond_nocam / cam_weight: the camera guidance term of ddim.py:268-280, cam_weight = (camera_cfg - 1) * scheduler weight."""
     x, e_cond, e_uncond, noise = (t.float() for t in (x, e_cond, e_uncond, noise))
     e = e_uncond + scale * (e_cond - e_uncond)
+    if e_cond_nocam is not None:
+        e = e + cam_weight * (e_cond - e_cond_nocam.float())
     if guidance_rescale > 0.0:
         dims = list(range(1, e.ndim))
         std_c = e_cond.std(dim=dims, keepdim=True)

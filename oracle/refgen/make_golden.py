@@ -365,6 +365,28 @@ def gen_vae(check):
         print(f"    encoder oracle vs reference: rel-L2 {rel_err(mo, mom)[0]:.3e}")
 
 
+def gen_camcfg(check):
+    """p_sample_ddim with camera guidance (camera_cfg = 2, cosine scheduler: a third UNet pass, ddim.py:268-280) on the small model."""
+    model = build_ref(SMALL_UNET, 128)
+    inp = synth_inputs(SMALL_CFG, SMALL_HW, 2, "small")
+    cam, F = camera_condition(model, 8 * SMALL_HW, "pan_yaw", inp["pluker"])
+    DDIM = rh.patch_ddim_for_cpu()
+    sampler = DDIM(model)
+    sampler.make_schedule(25, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
+    cond = {"c_crossattn": [inp["ctx_cond"]], "c_concat": [inp["c_concat"]], "camera_condition": cam}
+    uc = {"c_crossattn": [inp["ctx_uncond"]], "c_concat": [inp["c_concat"]]}
+    index = 9
+    step = int(sampler.ddim_timesteps[index])
+    ts = torch.full((1,), step, dtype=torch.long)
+    torch.manual_seed(20230211)
+    x_prev, pred_x0 = sampler.p_sample_ddim(inp["x"], cond, ts, index=index, unconditional_guidance_scale=3.5, unconditional_conditioning=uc,
+                                            guidance_rescale=0.7, fs=inp["fs"], enable_camera_condition=True, camera_cfg=2.0,
+                                            camera_cfg_scheduler="cosine")
+    print(f"  camera_cfg step: x_prev std {x_prev.std():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "camcfg_small.npz"), x_prev=x_prev.numpy(), pred_x0=pred_x0.numpy(), index=np.int64(index),
+                        t=np.int64(step), camera_cfg=np.float64(2.0))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -390,6 +412,9 @@ if __name__ == "__main__":
     if a.only in (None, "vae"):
         print("[vae]")
         gen_vae(a.check_oracle)
+    if a.only in (None, "camcfg"):
+        print("[camcfg]")
+        gen_camcfg(a.check_oracle)
     if a.only in ("unet_full",):
         print("[unet_full]")
         gen_unet_full(a.check_oracle)

@@ -152,6 +152,29 @@ def test_cfg_step_oracle_matches_reference_sampler(small):
     assert _rel(p0, torch.from_numpy(g["step_pred_x0"]))[0] < 1e-5
 
 
+def test_camera_guidance_step_oracle_matches_reference_sampler(small):
+    """p_sample_ddim with camera_cfg = 2 and the cosine scheduler (a third pass without the camera condition, ddim.py:268-280)."""
+    import math
+    cfg, orc, g, inp, cam = small
+    gc = np.load(os.path.join(GOLD, "camcfg_small.npz"))
+    index, step = int(gc["index"]), int(gc["t"])
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
+    t = torch.full((1,), step, dtype=torch.long)
+    e_c = orc.forward(xc, t, inp["ctx_cond"], inp["fs"], cam)
+    e_u = orc.forward(xc, t, inp["ctx_uncond"], inp["fs"], cam)
+    e_n = orc.forward(xc, t, inp["ctx_cond"], inp["fs"], None)
+    torch.manual_seed(20230211)
+    noise = torch.randn(inp["x"].shape)
+    s = ddim_oracle.ddim_schedule()
+    assert int(s["timesteps"][index]) == step
+    cam_w = (float(gc["camera_cfg"]) - 1.0) * math.cos((1.0 - step / 999.0) * math.pi / 2.0)
+    xp, p0 = ddim_oracle.cfg_ddim_update(inp["x"], e_c, e_u, noise, float(s["alphas"][index]), float(s["alphas_prev"][index]),
+                                         float(s["sigmas"][index]), float(s["sqrt_one_minus_alphas"][index]), 3.5, 0.7, e_cond_nocam=e_n,
+                                         cam_weight=cam_w)
+    assert _rel(xp, torch.from_numpy(gc["x_prev"]))[0] < 1e-5
+    assert _rel(p0, torch.from_numpy(gc["pred_x0"]))[0] < 1e-5
+
+
 def test_fused_epipolar_oracle_equals_explicit(small):
     cfg, orc, g, inp, cam = small
     from oracle.unet_oracle import UNetOracle

@@ -98,6 +98,35 @@ def test_small_cfg_step_vs_reference_sampler(small):
     assert torch.equal(xg, xp) and torch.equal(xg2, xp) and torch.equal(pg, p0)
 
 
+def test_small_camera_guidance_step_vs_reference_sampler(small):
+    """The reference's camera guidance (camera_cfg = 2, cosine scheduler; ddim.py:268-280): a third UNet pass without the camera
+    condition, e += (camera_cfg - 1) * w(t) * (e_cond - e_nocam) before the guidance rescale.  Golden: tests/golden/camcfg_small.npz."""
+    from camc2v_b200.sampler import DDIMSampler, DenoiserModel
+    cfg, unet, sd, g, inp, cam = small
+    gc = np.load(os.path.join(GOLD, "camcfg_small.npz"))
+    model = DenoiserModel(unet).to(DEV)
+    s = DDIMSampler(model)
+    s.make_schedule(25, "uniform_trailing", 1.0, verbose=False)
+    index = int(gc["index"])
+    assert int(s.ddim_timesteps[index]) == int(gc["t"])
+    ts = torch.full((1,), int(gc["t"]), dtype=torch.long, device=DEV)
+    torch.manual_seed(20230211)
+    noise = torch.randn(inp["x"].shape)
+    cond = {"c_crossattn": [inp["ctx_cond"].to(DEV)], "c_concat": [inp["c_concat"].to(DEV)], "camera_condition": cam}
+    uc = {"c_crossattn": [inp["ctx_uncond"].to(DEV)], "c_concat": [inp["c_concat"].to(DEV)]}
+    kw = dict(unconditional_guidance_scale=3.5, unconditional_conditioning=uc, guidance_rescale=0.7, fs=inp["fs"].to(DEV),
+              enable_camera_condition=True, noise=noise.to(DEV), camera_cfg=float(gc["camera_cfg"]), camera_cfg_scheduler="cosine")
+    xp, p0 = s.p_sample_ddim(inp["x"].to(DEV), cond, ts, index=index, **kw)
+    assert rel(xp, torch.from_numpy(gc["x_prev"]))[0] < TOL_L2
+    assert rel(p0, torch.from_numpy(gc["pred_x0"]))[0] < 2 * TOL_L2
+    xg, pg = s.p_sample_ddim(inp["x"].to(DEV), cond, ts, index=index, use_cuda_graph=True, **kw)
+    assert torch.equal(xg, xp) and torch.equal(pg, p0)
+    # camera_cfg = 1 is the two-pass step
+    kw["camera_cfg"] = 1.0
+    x1, _ = s.p_sample_ddim(inp["x"].to(DEV), cond, ts, index=index, **kw)
+    assert not torch.equal(x1, xp)
+
+
 def test_sampling_loop_runs_and_is_deterministic(small):
     from camc2v_b200.sampler import DDIMSampler, DenoiserModel
     cfg, unet, sd, g, inp, cam = small
