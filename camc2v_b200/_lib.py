@@ -70,6 +70,10 @@ PROTOTYPES = {
     "c2v_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "c2v_attention": (_i, [C.POINTER(AttnDesc), _vp]),
     "c2v_attention_temporal": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "c2v_attention_temporal_hd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "c2v_pixel_unshuffle_cl": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "c2v_avgpool2_cl": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "c2v_relu": (_i, [_vp, _i64, _vp]),
     "c2v_epipolar_mask": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_epipolar_mask_rect": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "c2v_epipolar_tile_map": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

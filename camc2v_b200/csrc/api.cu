@@ -318,6 +318,27 @@ int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int
     return attention_temporal_launch(qkv, out, B, T, HW, heads, (cudaStream_t)stream);
 }
 
+int c2v_attention_temporal_hd(const void* qkv, void* out, int B, int T, int HW, int heads, int head_dim, void* stream) {
+    if (!qkv || !out || B <= 0 || HW <= 0 || heads <= 0) return ERR_BAD_ARG;
+    return attention_temporal_hd_launch(qkv, out, B, T, HW, heads, head_dim, (cudaStream_t)stream);
+}
+
+int c2v_pixel_unshuffle_cl(const float* in, void* out, int B, int C, int T, int H, int W, int r, void* stream) {
+    if (!in || !out || B <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0) return ERR_BAD_ARG;
+    return pixel_unshuffle_cl_launch(in, out, B, C, T, H, W, r, (cudaStream_t)stream);
+}
+
+int c2v_avgpool2_cl(const float* in, float* out, void* out_16, int N, int H, int W, int C, void* stream) {
+    if (!in || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0) return ERR_BAD_ARG;
+    return avgpool2_cl_launch(in, out, out_16, N, H, W, C, (cudaStream_t)stream);
+}
+
+int c2v_relu(void* x, int64_t n, void* stream) {
+    if (!x || n < 0) return ERR_BAD_ARG;
+    if (n == 0) return OK;
+    return relu_launch(x, n, (cudaStream_t)stream);
+}
+
 int c2v_epipolar_mask(const float* F, uint8_t* out, int B, int T, int H, int W, int d, void* stream) {
     if (!F || !out) return ERR_BAD_ARG;
     return epipolar_mask_launch(F, out, B, T, T, H, W, d, (cudaStream_t)stream);

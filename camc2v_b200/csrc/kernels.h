@@ -31,6 +31,12 @@ int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, con
 // attn_t16.cu
 int attention_temporal_launch(const void* qkv, void* out, int B, int T, int HW, int heads, cudaStream_t st);
 
+// pose.cu
+int pixel_unshuffle_cl_launch(const float* in, void* out, int B, int C, int T, int H, int W, int r, cudaStream_t st);
+int avgpool2_cl_launch(const float* in, float* out, void* out_b, int N, int H, int W, int C, cudaStream_t st);
+int relu_launch(void* x, int64_t n, cudaStream_t st);
+int attention_temporal_hd_launch(const void* qkv, void* out, int B, int T, int HW, int heads, int D, cudaStream_t st);
+
 // epipolar.cu
 int epipolar_mask_launch(const float* F, uint8_t* out, int B, int T1, int T2, int H, int W, int d, cudaStream_t st);
 int plucker_launch(const float* K, const float* c2w, float* out, int B, int T, int H, int W, int plucker, cudaStream_t st);

@@ -219,6 +219,39 @@ def attention_temporal(qkv: torch.Tensor, B: int, T: int, HW: int, heads: int):
     return out
 
 
+def attention_temporal_hd(qkv: torch.Tensor, B: int, T: int, HW: int, heads: int, head_dim: int):
+    """qkv [B*T*HW, 3*heads*head_dim] (q | k | v) -> [B*T*HW, heads*head_dim]; any head dim % 8 == 0, <= 160 (pose encoder)."""
+    _chk(qkv, BF16, "attention_temporal_hd.qkv")
+    out = torch.empty((B * T * HW, heads * head_dim), device=qkv.device, dtype=BF16)
+    _lib.call("c2v_attention_temporal_hd", _p(qkv), _p(out), B, T, HW, heads, head_dim, _stream())
+    return out
+
+
+def pixel_unshuffle_cl(x: torch.Tensor, r: int):
+    """fp32 [B, C, T, H, W] -> 16-bit rows [(b, t, y, x), C*r*r] (rearrange + nn.PixelUnshuffle(r) + channel-last)."""
+    _chk(x, F32, "pixel_unshuffle_cl.x")
+    B, C_, T, H, W = x.shape
+    out = torch.empty((B * T * (H // r) * (W // r), C_ * r * r), device=x.device, dtype=BF16)
+    _lib.call("c2v_pixel_unshuffle_cl", _p(x), _p(out), B, C_, T, H, W, r, _stream())
+    return out
+
+
+def avgpool2_cl(x: torch.Tensor, N: int, H: int, W: int, want_16: bool = True):
+    """fp32 rows [N*H*W, C] -> (fp32 [N*H/2*W/2, C], the same in the operand dtype or None): nn.AvgPool2d(2, 2)."""
+    _chk(x, F32, "avgpool2_cl.x")
+    C_ = x.shape[1]
+    out = torch.empty((N * (H // 2) * (W // 2), C_), device=x.device, dtype=F32)
+    o16 = torch.empty(out.shape, device=x.device, dtype=BF16) if want_16 else None
+    _lib.call("c2v_avgpool2_cl", _p(x), _p(out), _p(o16), N, H, W, C_, _stream())
+    return out, o16
+
+
+def relu_(x: torch.Tensor):
+    _chk(x, BF16, "relu_.x")
+    _lib.call("c2v_relu", _p(x), x.numel(), _stream())
+    return x
+
+
 # ------------------------------------------------------------------------------------------------ camera
 def epipolar_mask(F: torch.Tensor, H: int, W: int, d: int) -> torch.Tensor:
     """F fp32 [B,T1,T2,3,3] -> bool [B, T1*H*W, T2*H*W] (camcontexti2v.py:202-271), bit-exact.  T1 = T2 for the UNet's temporal

@@ -145,6 +145,23 @@ int c2v_attention(const c2v_attn_desc* d, void* stream);
 int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int heads, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Camera pose encoder (SURVEY f-2; CamContextI2V/model/modules/camera_pose_encoder.py:295-376): the ops the UNet path does
+ * not already provide.  16-bit tensors are in the library's operand dtype (c2v_operand_dtype).
+ * -----------------------------------------------------------------------------------------------*/
+/* Temporal self-attention with head dim `head_dim` (multiple of 8, <= 160; 320/8, 640/8, 1280/8 in the shipped config) over
+ * T <= 16 frames: diffusers Attention / AttnProcessor2_0 as used by TemporalSelfAttention (camera_pose_encoder.py:101-160).
+ * qkv [B, T, HW, 3*heads*head_dim] packed (q | k | v), out [B, T, HW, heads*head_dim]. */
+int c2v_attention_temporal_hd(const void* qkv, void* out, int B, int T, int HW, int heads, int head_dim, void* stream);
+/* rearrange 'b c f h w -> (b f) c h w' + nn.PixelUnshuffle(r) (camera_pose_encoder.py:359-361): fp32 [B, C, T, H, W] ->
+ * 16-bit channel-last rows [(b, f, y, x), C*r*r], channel = c*r*r + dy*r + dx. */
+int c2v_pixel_unshuffle_cl(const float* in, void* out, int B, int C, int T, int H, int W, int r, void* stream);
+/* nn.AvgPool2d(2, 2) (Downsample with use_conv=False, camera_pose_encoder.py:212-231) on channel-last fp32 rows [N, H, W, C];
+ * out fp32 [N, H/2, W/2, C], out_16 (optional) the same in the operand dtype. */
+int c2v_avgpool2_cl(const float* in, float* out, void* out_16, int N, int H, int W, int C, void* stream);
+/* in-place ReLU (ResnetBlock.act, camera_pose_encoder.py:262) on n 16-bit values, n % 8 == 0. */
+int c2v_relu(void* x, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Camera geometry.
  * ---------------------------------------------------------------------------------------------- */
 /* Materialise the epipolar mask (camcontexti2v.py:202-271): F fp32 [B,T,T,3,3] -> uint8 [B, T*H*W, T*H*W]. Bit-exact. */

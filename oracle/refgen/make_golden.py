@@ -365,6 +365,44 @@ def gen_vae(check):
         print(f"    encoder oracle vs reference: rel-L2 {rel_err(mo, mom)[0]:.3e}")
 
 
+POSE_KW = dict(downscale_factor=8, channels=[320, 640], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
+               temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+               temporal_position_encoding_max_len=16)
+
+
+def gen_pose_encoder(check):
+    """CameraPoseEncoder (SURVEY f-2) in the shipped configuration (camcontexti2v_256.yaml:125-139) cut to its first two levels
+    (head dims 40 and 80), on the Pluecker embedding of a 64 x 64 orbit trajectory.  The reference class itself runs; the two
+    `diffusers` classes it imports are the restated stand-ins of oracle/refgen/diffusers_stub.py (diffusers is not installed)."""
+    import json
+    import oracle
+    from oracle import camera_oracle, pose_encoder_oracle
+    import diffusers_stub
+    diffusers_stub.install()
+    rh.setup_reference_imports()
+    from model.modules.camera_pose_encoder import CameraPoseEncoder
+    torch.manual_seed(0)
+    ref = CameraPoseEncoder(**POSE_KW).eval()
+    pe = {k: v.clone() for k, v in ref.state_dict().items() if k.endswith("pos_encoder.pe")}
+    synth.fill_module_(ref, seed=8)
+    ref.load_state_dict(pe, strict=False)                    # keep the sinusoidal buffers the constructor made
+    K, w2c = synth.synth_camera("orbit", T=16, H=64, W=64, B=1)
+    rel = camera_oracle.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))
+    x = oracle.plucker(K, rel, 64, 64, "plucker")            # == CameraControlLVDM.ray_condition (tests/test_oracle_golden.py)
+    with torch.no_grad():
+        feats = ref(x)
+    print("  pose encoder:", [tuple(f.shape) for f in feats], [round(float(f.std()), 4) for f in feats])
+    np.savez_compressed(os.path.join(GOLD, "pose_encoder_small.npz"), **{f"f{i}": f.numpy() for i, f in enumerate(feats)},
+                        kwargs=json.dumps(POSE_KW))
+    json.dump({k: list(v.shape) for k, v in ref.state_dict().items()}, open(os.path.join(GOLD, "state_dict_pose_encoder.json"), "w"), indent=0)
+    for k, v in pe.items():
+        d = v.shape[-1]
+        assert torch.equal(v[0], pose_encoder_oracle.positional_encoding(d, 16)), k
+    if check:
+        fo = pose_encoder_oracle.pose_encoder_forward(ref.state_dict(), x, n_levels=2)
+        print("    oracle vs reference rel-L2:", [f"{rel_err(a, b)[0]:.3e}" for a, b in zip(fo, feats)])
+
+
 def gen_camcfg(check):
     """p_sample_ddim with camera guidance (camera_cfg = 2, cosine scheduler: a third UNet pass, ddim.py:268-280) on the small model."""
     model = build_ref(SMALL_UNET, 128)
@@ -412,6 +450,9 @@ if __name__ == "__main__":
     if a.only in (None, "vae"):
         print("[vae]")
         gen_vae(a.check_oracle)
+    if a.only in (None, "pose_encoder"):
+        print("[pose_encoder]")
+        gen_pose_encoder(a.check_oracle)
     if a.only in (None, "camcfg"):
         print("[camcfg]")
         gen_camcfg(a.check_oracle)

@@ -292,3 +292,40 @@ def test_vae_encoder_oracle_matches_reference():
     mom = vae_oracle.encode_moments(sd, x, dd["ch_mult"], dd["num_res_blocks"])
     l2, mx = _rel(mom, torch.from_numpy(g["moments"]))
     assert l2 < 1e-5 and mx < 1e-5, (l2, mx)
+
+
+# ------------------------------------------------------------------------------------------------ camera pose encoder (SURVEY f-2)
+def _pose_inputs():
+    from oracle import camera_oracle
+    K, w2c = synth.synth_camera("orbit", T=16, H=64, W=64, B=1)
+    rel = camera_oracle.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))
+    return oracle.plucker(K, rel, 64, 64, "plucker")
+
+
+def pose_state_dict(kw, seed=8):
+    """Synthetic parameters + the sinusoidal `pos_encoder.pe` buffers the constructor makes (what the golden generator used)."""
+    from camc2v_b200.pose_encoder import CameraPoseEncoder
+    from oracle import pose_encoder_oracle
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in CameraPoseEncoder(**kw).state_dict().items()}
+    sd = synth.synth_state_dict(shapes, seed)
+    for k, s in shapes.items():
+        if k.endswith("pos_encoder.pe"):
+            sd[k] = pose_encoder_oracle.positional_encoding(s[2], s[1])[None]
+    return shapes, sd
+
+
+def test_pose_encoder_oracle_matches_reference():
+    """oracle/pose_encoder_oracle.py against the reference's own CameraPoseEncoder (golden made with the restated diffusers stand-ins:
+    parity pinned for the reference file, unpinned for diffusers' Attention / FeedForward - see the oracle's header)."""
+    import json
+    from oracle import pose_encoder_oracle
+    g = np.load(os.path.join(GOLD, "pose_encoder_small.npz"))
+    kw = json.loads(str(g["kwargs"]))
+    shapes, sd = pose_state_dict(kw)
+    assert {k: list(v) for k, v in shapes.items()} == json.load(open(os.path.join(GOLD, "state_dict_pose_encoder.json")))   # drop-in state_dict
+    feats = pose_encoder_oracle.pose_encoder_forward(sd, _pose_inputs(), n_levels=len(kw["channels"]), nums_rb=kw["nums_rb"],
+                                                     heads=kw["temporal_attention_nhead"], n_attn=len(kw["attention_block_types"]))
+    for i, f in enumerate(feats):
+        l2, mx = _rel(f, torch.from_numpy(g[f"f{i}"]))
+        assert l2 < 1e-5 and mx < 1e-5, (i, l2, mx)

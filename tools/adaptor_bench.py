@@ -103,6 +103,44 @@ def resampler_main():
     print(json.dumps(line))
 
 
+def pose_encoder_main():
+    """CameraPoseEncoder at the shipped size (camcontexti2v_256.yaml:125-139): Pluecker embedding [1, 6, 16, 256, 256] -> 4 feature maps."""
+    from camc2v_b200.pose_encoder import CameraPoseEncoder
+    dev = torch.device("cuda", 0)
+    kw = dict(downscale_factor=8, channels=[320, 640, 1280, 1280], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
+              temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+              temporal_position_encoding_max_len=16)
+    m = CameraPoseEncoder(**kw)
+    pe = {k: v.clone() for k, v in m.state_dict().items() if k.endswith("pos_encoder.pe")}
+    synth.fill_module_(m, seed=8)
+    m.load_state_dict(pe, strict=False)
+    m = m.to(dev)
+    K, w2c = synth.synth_camera("orbit", T=16, H=256, W=256, B=1)
+    from camc2v_b200 import camera
+    x = ops.plucker(K.to(dev), camera.relative_c2w(w2c, torch.zeros(1, dtype=torch.long)).to(dev), 256, 256)
+    for _ in range(2):
+        y = m(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        y = m(x)
+    e1.record()
+    torch.cuda.synchronize()
+    line = {"metric": "pose_encoder_ms_per_sample", "value": e0.elapsed_time(e1) / 10,
+            "unit": "ms (CameraPoseEncoder forward, [1,6,16,256,256] -> 320x32x32 / 640x16x16 / 1280x8x8 / 1280x4x4 per frame)",
+            "finite": bool(all(torch.isfinite(f).all() for f in y)), "shapes": [list(f.shape) for f in y], "dtype": ops._lib.OPERANDS}
+    if "--no-cpu" not in sys.argv:
+        from oracle import pose_encoder_oracle
+        sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+        t0 = time.perf_counter()
+        fo = pose_encoder_oracle.pose_encoder_forward(sd, x.cpu())
+        line["cpu_baseline"] = {"value": (time.perf_counter() - t0) * 1e3, "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "oracle (CPU port of the reference, fp32), whole forward"}
+        line["rel_l2_vs_oracle"] = [float((a.cpu().double() - b.double()).norm() / b.double().norm()) for a, b in zip(y, fo)]
+    print(json.dumps(line))
+
+
 def vae_main():
     """decode_first_stage at the shipped size (camcontexti2v_256.yaml:74-93): 16 latent frames [4, 32, 32] -> 16 x [3, 256, 256]."""
     from camc2v_b200.vae import AutoencoderKLDecoder
@@ -149,5 +187,7 @@ if __name__ == "__main__":
         vae_main()
     elif "--resampler" in sys.argv:
         resampler_main()
+    elif "--pose-encoder" in sys.argv:
+        pose_encoder_main()
     else:
         main()

@@ -1,11 +1,11 @@
 """One whole CamContextI2V sample on the B200 kernels, stage by stage (synthetic weights and inputs, shipped sizes):
 
     Resampler (image tokens of the reference + 2 context frames)  ->  conditional epipolar mask + MultiLatentEpipolarAdaptor (c_concat)
-    ->  camera condition (F, tile maps, packed masks)  ->  25-step DDIM sampling with CFG (CUDA graph)  ->  VAE decode to 16 RGB frames
+    ->  Pluecker embedding + CameraPoseEncoder (pluker_embedding_features)  ->  camera condition (F, tile maps, packed masks)  ->  25-step DDIM sampling with CFG (CUDA graph)  ->  VAE decode to 16 RGB frames
 
     python tools/sample_video.py [--steps 25]
 Prints one JSON line with the time of every stage (CUDA events / host clock around synchronised stages).  The CLIP encoders, the
-VAE *encoding* of the input frames and the CameraPoseEncoder are outside (their outputs are synthetic tensors of the right shape).
+VAE *encoding* of the input frames are outside (their outputs are synthetic tensors of the right shape).
 """
 import argparse
 import json
@@ -22,6 +22,7 @@ from camc2v_b200 import camera, ops, synth  # noqa: E402
 from camc2v_b200.adaptor import MultiLatentEpipolarAdaptor  # noqa: E402
 from camc2v_b200.config import UNetConfig  # noqa: E402
 from camc2v_b200.modules import build_unet  # noqa: E402
+from camc2v_b200.pose_encoder import CameraPoseEncoder  # noqa: E402
 from camc2v_b200.resampler import Resampler  # noqa: E402
 from camc2v_b200.sampler import DDIMSampler, DenoiserModel  # noqa: E402
 from camc2v_b200.vae import AutoencoderKLDecoder  # noqa: E402
@@ -65,20 +66,33 @@ def main():
     clip_img = synth.synth_tensor("sample.clip", (3, 257, 1280), 1).to(dev)          # reference frame + 2 context frames
     text = synth.synth_tensor("sample.text", (1, 77, 1024), 2).to(dev)
     z_cond = synth.synth_tensor("sample.zcond", (1, 3 * 1024, 4), 3).to(dev)           # their VAE latents as tokens
-    pluker = [synth.synth_tensor(f"sample.pl{i}", (1, c, 16, 32 >> i, 32 >> i), 4, std=0.1).to(dev) for i, c in enumerate((320, 640, 1280, 1280))]
+    pose_enc = CameraPoseEncoder(downscale_factor=8, channels=[320, 640, 1280, 1280], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False,
+                                 compression_factor=1, temporal_attention_nhead=8, attention_block_types=["Temporal_Self"],
+                                 temporal_position_encoding=True, temporal_position_encoding_max_len=16)
+    pe = {k: v.clone() for k, v in pose_enc.state_dict().items() if k.endswith("pos_encoder.pe")}
+    synth.fill_module_(pose_enc, seed=8)
+    pose_enc.load_state_dict(pe, strict=False)
+    pose_enc = pose_enc.to(dev)
     x_T = synth.synth_tensor("sample.xT", (1, 4, 16, 32, 32), 5).to(dev)
     fs = torch.full((1,), 3, dtype=torch.long, device=dev)
     cond_idx = torch.zeros(1, dtype=torch.long)
     stages = {}
+
+    def run_pose():      # camcontexti2v.py:556-561: ray_condition -> pose_encoder -> '(b f) c h w -> b c f h w'
+        pl = ops.plucker(K.to(dev), camera.relative_c2w(w2c, cond_idx).to(dev), 256, 256)
+        return [f.view(1, 16, f.shape[1], f.shape[2], f.shape[3]).permute(0, 2, 1, 3, 4).contiguous() for f in pose_enc(pl)]
 
     def warm():          # builds the weight packs of every module once (not part of a sample)
         resampler(clip_img)
         m = ops.epipolar_mask(camera.conditional_fundamental_matrices(K, w2c, w2c_cond, cond_idx).to(dev), 32, 32, 8)
         adaptor(z_cond, m)
         vae.decode(x_T[0].permute(1, 0, 2, 3).contiguous())
+        run_pose()
+
     warm()
 
     img_tok, stages["resampler_ms"] = timed(lambda: resampler(clip_img))              # [3, 256, 1024]
+    pluker, stages["plucker_and_pose_encoder_ms"] = timed(run_pose)
 
     def run_adaptor():
         Fm = camera.conditional_fundamental_matrices(K, w2c, w2c_cond, cond_idx).to(dev)
