@@ -57,7 +57,7 @@ int c2v_gemm_splitk(int M, int N, int Cin, int taps, int epi) {
     const int bn = c2v_gemm_tile_n(N, epi);
     const int ctas = ((M + 127) / 128) * ((N + bn - 1) / bn);
     const int iters = taps * (Cin / 64);
-    if (ctas >= 200 || iters < 30) return 1;
+    if (ctas >= 120 || iters < 30) return 1;   // >= 0.8 wave of tiles already: the reduce pass costs more than the idle SMs
     int s = (296 + ctas / 2) / ctas;           // round to the nearest multiple of one full wave
     if (s > 8) s = 8;
     if (s > iters / 15) s = iters / 15;
@@ -100,6 +100,7 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     a.splits = d->splitk > 1 ? d->splitk : 1;
     if (a.splits > 1) {
         if (d->epi != C2V_EPI_LINEAR || a.splits > a.taps * a.k_chunks) return ERR_BAD_ARG;
+        if (a.splits > 8) return ERR_UNSUPPORTED;
         if (!d->ws) {
             // no workspace: the splits of a tile run as one thread-block cluster (<= 8 CTAs) and reduce through DSMEM
             if (a.splits > 8 || d->ldo % 4 != 0 || (d->residual && d->ldr % 4 != 0)) return ERR_UNSUPPORTED;

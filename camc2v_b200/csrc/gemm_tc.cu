@@ -502,22 +502,29 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int m = (int)(i / nv);
         const int n = (int)(i - (long long)m * nv) * 4;
-        float4 x = *reinterpret_cast<const float4*>(ws + (size_t)m * N + n);
-        for (int z = 1; z < splits; ++z) {
-            const float4 y = *reinterpret_cast<const float4*>(ws + z * plane + (size_t)m * N + n);
-            x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+        // every operand of the element is requested before the first add: one memory round trip per element (splits <= 8)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 y[8];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) y[z] = z < splits ? *reinterpret_cast<const float4*>(ws + z * plane + (size_t)m * N + n) : z4;
+        const float4 b0 = bias ? *reinterpret_cast<const float4*>(bias + n) : z4;
+        const float4 b1 = rowbias ? *reinterpret_cast<const float4*>(rowbias + (size_t)(m / rows_per_group) * N + n) : z4;
+        const float4 b2 = residual ? *reinterpret_cast<const float4*>(residual + (size_t)m * ldr + n) : z4;
+        float4 x = y[0];
+#pragma unroll
+        for (int z = 1; z < 8; ++z) {
+            if (z < splits) {
+                x.x += y[z].x; x.y += y[z].y; x.z += y[z].z; x.w += y[z].w;
+            }
         }
         if (bias) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + n);
-            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            x.x += b0.x; x.y += b0.y; x.z += b0.z; x.w += b0.w;
         }
         if (rowbias) {
-            const float4 b = *reinterpret_cast<const float4*>(rowbias + (size_t)(m / rows_per_group) * N + n);
-            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            x.x += b1.x; x.y += b1.y; x.z += b1.z; x.w += b1.w;
         }
         if (residual) {
-            const float4 b = *reinterpret_cast<const float4*>(residual + (size_t)m * ldr + n);
-            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            x.x += b2.x; x.y += b2.y; x.z += b2.z; x.w += b2.w;
         }
         if (out_bf16)
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)m * ldo + n) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
@@ -528,6 +535,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 
 int splitk_reduce_launch(const float* ws, int splits, int M, int N, const float* bias, const float* rowbias, int rows_per_group,
                          const float* residual, int ldr, void* out, int ldo, int out_bf16, cudaStream_t st) {
+    if (splits > 8) return ERR_UNSUPPORTED;
     long long work = (long long)M * (N >> 2);
     int grid = (int)((work + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;

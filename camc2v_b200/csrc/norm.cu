@@ -63,23 +63,18 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_stats_kernel(const float* __
             const size_t step = (size_t)m.rows_par * C;
             int r = r0 + m.rsub;
             // 4 independent 16-byte loads in flight per thread
-            for (; r + 3 * m.rows_par < r1; r += 4 * m.rows_par) {
+            // the last batch is predicated (zero rows add nothing) rather than walked row by row: one round trip, not up to three
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (; r < r1; r += 4 * m.rows_par) {
                 const float* p0 = col + (size_t)r * C;
                 const float4 v0 = *reinterpret_cast<const float4*>(p0);
-                const float4 v1 = *reinterpret_cast<const float4*>(p0 + step);
-                const float4 v2 = *reinterpret_cast<const float4*>(p0 + 2 * step);
-                const float4 v3 = *reinterpret_cast<const float4*>(p0 + 3 * step);
+                const float4 v1 = r + m.rows_par < r1 ? *reinterpret_cast<const float4*>(p0 + step) : z4;
+                const float4 v2 = r + 2 * m.rows_par < r1 ? *reinterpret_cast<const float4*>(p0 + 2 * step) : z4;
+                const float4 v3 = r + 3 * m.rows_par < r1 ? *reinterpret_cast<const float4*>(p0 + 3 * step) : z4;
                 a[0] += (v0.x + v1.x) + (v2.x + v3.x); q[0] += fmaf(v0.x, v0.x, v1.x * v1.x) + fmaf(v2.x, v2.x, v3.x * v3.x);
                 a[1] += (v0.y + v1.y) + (v2.y + v3.y); q[1] += fmaf(v0.y, v0.y, v1.y * v1.y) + fmaf(v2.y, v2.y, v3.y * v3.y);
                 a[2] += (v0.z + v1.z) + (v2.z + v3.z); q[2] += fmaf(v0.z, v0.z, v1.z * v1.z) + fmaf(v2.z, v2.z, v3.z * v3.z);
                 a[3] += (v0.w + v1.w) + (v2.w + v3.w); q[3] += fmaf(v0.w, v0.w, v1.w * v1.w) + fmaf(v2.w, v2.w, v3.w * v3.w);
-            }
-            for (; r < r1; r += m.rows_par) {
-                const float4 v = *reinterpret_cast<const float4*>(col + (size_t)r * C);
-                a[0] += v.x; q[0] = fmaf(v.x, v.x, q[0]);
-                a[1] += v.y; q[1] = fmaf(v.y, v.y, q[1]);
-                a[2] += v.z; q[2] = fmaf(v.z, v.z, q[2]);
-                a[3] += v.w; q[3] = fmaf(v.w, v.w, q[3]);
             }
             const int g0 = (cv * 4) / cg, g3 = (cv * 4 + 3) / cg;
             if (g0 == g3) {
@@ -168,15 +163,19 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_apply_kernel(const float* __
             *reinterpret_cast<uint2*>(ocol + off) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
         };
         int r = r0 + m.rsub;
-        for (; r + 3 * m.rows_par < r1; r += 4 * m.rows_par) {
+        for (; r < r1; r += 4 * m.rows_par) {      // last batch predicated: one round trip instead of a row-by-row tail
             const size_t o0 = (size_t)r * C;
+            const bool k1 = r + m.rows_par < r1, k2 = r + 2 * m.rows_par < r1, k3 = r + 3 * m.rows_par < r1;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 v0 = *reinterpret_cast<const float4*>(col + o0);
-            const float4 v1 = *reinterpret_cast<const float4*>(col + o0 + step);
-            const float4 v2 = *reinterpret_cast<const float4*>(col + o0 + 2 * step);
-            const float4 v3 = *reinterpret_cast<const float4*>(col + o0 + 3 * step);
-            emit(v0, o0); emit(v1, o0 + step); emit(v2, o0 + 2 * step); emit(v3, o0 + 3 * step);
+            const float4 v1 = k1 ? *reinterpret_cast<const float4*>(col + o0 + step) : z4;
+            const float4 v2 = k2 ? *reinterpret_cast<const float4*>(col + o0 + 2 * step) : z4;
+            const float4 v3 = k3 ? *reinterpret_cast<const float4*>(col + o0 + 3 * step) : z4;
+            emit(v0, o0);
+            if (k1) emit(v1, o0 + step);
+            if (k2) emit(v2, o0 + 2 * step);
+            if (k3) emit(v3, o0 + 3 * step);
         }
-        for (; r < r1; r += m.rows_par) emit(*reinterpret_cast<const float4*>(col + (size_t)r * C), (size_t)r * C);
     }
 }
 
@@ -219,54 +218,71 @@ int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta,
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 10;   // float4 per lane -> C <= 1280
 
+// Each warp walks rows row0, row0 + stride, ...; the loads of the next row are issued before the statistics of the current
+// one, so a warp keeps two rows of traffic in flight (a one-row-per-warp grid is latency-bound: 2.9 TB/s at 16384 x 320).
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ add, __nv_bfloat16* __restrict__ out2,
                                                         float* __restrict__ out_f32, int rows, int C, float eps) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int wpb = blockDim.x >> 5, stride = gridDim.x * wpb;
+    int row = blockIdx.x * wpb + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const int nvec = C >> 2;
-    const float* xr = x + (size_t)row * C;
-    float4 v[LN_MAXV];
-    float s = 0.f;
+    float4 v[NV], nx[NV];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int cv = lane + i * 32;
-        if (cv < nvec) {
-            v[i] = *reinterpret_cast<const float4*>(xr + cv * 4);
-            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        }
+        if (cv < nvec) v[i] = *reinterpret_cast<const float4*>(x + (size_t)row * C + cv * 4);
     }
-    const float mean = warp_sum(s) / (float)C;
-    float q = 0.f;
+    for (; row < rows; row += stride) {
+        const int nrow = row + stride;
+        if (nrow < rows) {
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int cv = lane + i * 32;
-        if (cv < nvec) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int cv = lane + i * 32;
-        if (cv < nvec) {
-            const float4 g = *reinterpret_cast<const float4*>(gamma + cv * 4);
-            const float4 bb = *reinterpret_cast<const float4*>(beta + cv * 4);
-            const float y0 = (v[i].x - mean) * rstd * g.x + bb.x;
-            const float y1 = (v[i].y - mean) * rstd * g.y + bb.y;
-            const float y2 = (v[i].z - mean) * rstd * g.z + bb.z;
-            const float y3 = (v[i].w - mean) * rstd * g.w + bb.w;
-            *reinterpret_cast<uint2*>(out + (size_t)row * C + cv * 4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
-            if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * C + cv * 4) = make_float4(y0, y1, y2, y3);
-            if (add) {
-                const float4 p = *reinterpret_cast<const float4*>(add + (size_t)row * C + cv * 4);
-                *reinterpret_cast<uint2*>(out2 + (size_t)row * C + cv * 4) =
-                    make_uint2(pack_bf16(y0 + p.x, y1 + p.y), pack_bf16(y2 + p.z, y3 + p.w));
+            for (int i = 0; i < NV; ++i) {
+                const int cv = lane + i * 32;
+                if (cv < nvec) nx[i] = *reinterpret_cast<const float4*>(x + (size_t)nrow * C + cv * 4);
             }
         }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int cv = lane + i * 32;
+            if (cv < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int cv = lane + i * 32;
+            if (cv < nvec) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int cv = lane + i * 32;
+            if (cv < nvec) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + cv * 4));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + cv * 4));
+                const float y0 = (v[i].x - mean) * rstd * g.x + bb.x;
+                const float y1 = (v[i].y - mean) * rstd * g.y + bb.y;
+                const float y2 = (v[i].z - mean) * rstd * g.z + bb.z;
+                const float y3 = (v[i].w - mean) * rstd * g.w + bb.w;
+                *reinterpret_cast<uint2*>(out + (size_t)row * C + cv * 4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * C + cv * 4) = make_float4(y0, y1, y2, y3);
+                if (add) {
+                    const float4 p = *reinterpret_cast<const float4*>(add + (size_t)row * C + cv * 4);
+                    *reinterpret_cast<uint2*>(out2 + (size_t)row * C + cv * 4) =
+                        make_uint2(pack_bf16(y0 + p.x, y1 + p.y), pack_bf16(y2 + p.z, y3 + p.w));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = nx[i];
     }
 }
 
@@ -274,9 +290,19 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
                      int rows, int C, float eps, cudaStream_t st) {
     if (C % 4 != 0 || (C >> 2) > LN_MAXV * 32 || rows <= 0) return ERR_UNSUPPORTED;
     if (add && !out2) return ERR_BAD_ARG;
-    const int wpb = 8;
-    layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), add,
-                                                                 reinterpret_cast<__nv_bfloat16*>(out2), out_f32, rows, C, eps);
+    const int nv = ((C >> 2) + 31) / 32;
+    // few rows: 4-warp CTAs, one row per warp, spread over all SMs; many rows: 8-warp CTAs, 4 per SM, each warp walking its rows
+    const int wpb = rows <= 148 * 8 * 2 ? 4 : 8;
+    int grid = (rows + wpb - 1) / wpb;
+    if (grid > 148 * 4) grid = 148 * 4;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(out2);
+    if (nv <= 3)
+        layernorm_kernel<3><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, o, add, o2, out_f32, rows, C, eps);
+    else if (nv <= 5)
+        layernorm_kernel<5><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, o, add, o2, out_f32, rows, C, eps);
+    else
+        layernorm_kernel<LN_MAXV><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, o, add, o2, out_f32, rows, C, eps);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -60,7 +60,7 @@ def test_linear(M, N, K):
     close(res2, ref, 2e-3, "linear in-place")
 
 
-@pytest.mark.parametrize("M,N,K,bf16", [(256, 1280, 5120, False), (1024, 1280, 5120, True), (4096, 640, 2560, False), (200, 1280, 3840, False)])
+@pytest.mark.parametrize("M,N,K,bf16", [(256, 1280, 5120, False), (1024, 1280, 5120, True), (2048, 640, 2560, False), (200, 1280, 3840, False)])
 def test_splitk_cluster_reduce_matches_workspace_path(M, N, K, bf16):
     """Split-K through a thread-block cluster (partials reduced in distributed shared memory, ws = NULL) against the
     workspace + reduce-kernel path (the default): same fixed summation order over the splits -> identical bits; and
