@@ -237,6 +237,18 @@ class TimestepBlock(nn.Module):
     pass
 
 
+BATCH_EMB = os.environ.get("C2V_EMB_BATCH", "1") != "0"      # 0: every ResBlock projects the embedding itself (26 launches per pass)
+
+
+class EmbPack:
+    """Timestep embedding of a pass plus the emb_layers projections of ALL ResBlocks, computed by one skinny GEMM at the top
+    of UNetModel.forward (26 launches per pass folded into one): block i reads columns [off, off + Cout) of `all`."""
+    __slots__ = ("raw", "all")
+
+    def __init__(self, raw: torch.Tensor, all_: torch.Tensor):
+        self.raw, self.all = raw, all_
+
+
 class ResBlock(_Prepared, TimestepBlock):
     """openaimodel3d.py:109-236 (no scale-shift norm, no up/down, 1x1 skip when channels change)."""
 
@@ -275,7 +287,14 @@ class ResBlock(_Prepared, TimestepBlock):
         """h fp32 CL [M, Cin]; emb fp32 [B, emb_channels] (identical for the T frames of a sample, modified_forwards.py:45)."""
         p = self.pk()
         n = ops.groupnorm(h, p["g1"], p["be1"], dm.BT, dm.HW, 1e-5, True)
-        e = ops.skinny_linear(emb, p["we"], p["bemb"], True)                        # Linear(SiLU(emb)) -> [B, Cout]
+        sl = getattr(self, "_emb_slice", None)
+        if isinstance(emb, EmbPack) and sl is not None:                             # projected by UNetModel.forward for all blocks at once
+            e = emb.all[:, sl[0]:sl[0] + sl[1]]
+            if e.shape[0] > 1:
+                e = e.contiguous()
+        else:
+            raw = emb.raw if isinstance(emb, EmbPack) else emb
+            e = ops.skinny_linear(raw, p["we"], p["bemb"], True)                    # Linear(SiLU(emb)) -> [B, Cout]
         h1 = ops.conv3x3(n, p["w1"], dm.BT, dm.H, dm.W, bias=p["b1"], rowbias=e, rows_per_group=dm.T * dm.HW)
         n = ops.groupnorm(h1, p["g2"], p["be2"], dm.BT, dm.HW, 1e-5, True)
         if "ws" in p:
@@ -1070,6 +1089,14 @@ class UNetModel(_Prepared):
              "g_out": _f32(self.out[0].weight), "be_out": _f32(self.out[0].bias), "w_out": wo, "b_out": bo}
         for name, seq in (("t", self.time_embed), ("f", self.fps_embedding)):
             p[name] = (_bf16(seq[0].weight), _f32(seq[0].bias), _bf16(seq[2].weight), _f32(seq[2].bias))
+        # emb_layers of every ResBlock (openaimodel3d.py:161-167) stacked into one [sum Cout, 4*mc] matrix
+        blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+        off = 0
+        for blk in blocks:
+            blk._emb_slice = (off, blk.out_channels)
+            off += blk.out_channels
+        p["we_all"] = _bf16(torch.cat([blk.emb_layers[1].weight.detach() for blk in blocks], dim=0))
+        p["bemb_all"] = _f32(torch.cat([blk.emb_layers[1].bias.detach() for blk in blocks], dim=0))
         return p
 
     def _embed(self, seq_key: str, idx: torch.Tensor):
@@ -1104,6 +1131,8 @@ class UNetModel(_Prepared):
             if fs is None:
                 fs = torch.full((b,), self.default_fs, dtype=torch.long, device=dev)
             emb = emb + self._embed("f", fs.to(dev))                                  # [B, 4*mc] (tiny; identical for all T frames)
+        if BATCH_EMB:
+            emb = EmbPack(emb, ops.skinny_linear(emb, p["we_all"], p["bemb_all"], True))
         ctx = make_context_pack(context.to(dev), t)
         dm = Dims(b, t, hh, ww)
 
