@@ -444,7 +444,8 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
                 }
             }
             // ---- pass 2: probabilities, written straight into the 128B-swizzled K-major P tile of the PV MMA ----
-            float l0 = 0.f, l1 = 0.f;
+            float2 l2 = make_float2(0.f, 0.f);
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
             for (int c = 0; c < AT_BN / 32; ++c) {
                 if ((anyc >> c) & 1u) {
@@ -456,11 +457,11 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
                         uint32_t w[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float e0 = fast_exp2(__fmaf_rn(__uint_as_float(v[g * 8 + 2 * i]), p.scale_log2, -m_use));
-                            const float e1 = fast_exp2(__fmaf_rn(__uint_as_float(v[g * 8 + 2 * i + 1]), p.scale_log2, -m_use));
-                            l0 += e0;
-                            l1 += e1;
-                            w[i] = pack_bf16(e0, e1);
+                            // pass 2 is issue-bound: the scale-and-shift and the row sums go two elements per instruction
+                            const float2 x = ffma2(make_float2(__uint_as_float(v[g * 8 + 2 * i]), __uint_as_float(v[g * 8 + 2 * i + 1])), sc2, nm2);
+                            const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                            l2 = fadd2(l2, e);
+                            w[i] = pack_bf16(e.x, e.y);
                         }
                         *reinterpret_cast<uint4*>(p_row + (((c * 4 + g) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
                     for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(p_row + (((c * 4 + g) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
-            l_run += l0 + l1;
+            l_run += l2.x + l2.y;
             m_run = m_new;
             fence_proxy_async();
             tc_fence_before();
