@@ -241,10 +241,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 2) gemm_tc_kernel(const _
                     }
                 }
                 if (rb) {
+                    if (nb + 32 <= p.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(rb + nb + j);
-                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(rb + nb + j);
+                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        }
+                    } else {                                          // ragged last N tile: never read past the row of the row bias
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.N) f[j] += rb[nb + j];
                     }
                 }
                 if (p.epi == EPI_GELU && !part) {
