@@ -217,6 +217,7 @@ class DDIMSampler(object):
         camera_cfg_scheduler = kwargs.pop("camera_cfg_scheduler", "constant")
         if camera_cfg_scheduler not in ("constant", "cosine"):
             raise NotImplementedError(camera_cfg_scheduler)
+        e_nc, cam_w = None, 0.0
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
             e_c = self.model.apply_model(x, t, c, **kwargs)
             e_u, scale, phi = e_c, 1.0, 0.0
@@ -227,7 +228,6 @@ class DDIMSampler(object):
                 cam = c.get("camera_condition")
                 if cam is not None and uc.get("camera_condition") is not cam:
                     uc["camera_condition"] = cam
-            e_nc, cam_w = None, 0.0
             if camera_cfg != 1.0 and kwargs.get("enable_camera_condition", False) and isinstance(c, dict):
                 # camera guidance (ddim.py:268-280): a third pass, conditional but without the camera condition
                 if self.cfg_pair is not None:

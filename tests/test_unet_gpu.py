@@ -127,6 +127,29 @@ def test_small_camera_guidance_step_vs_reference_sampler(small):
     assert not torch.equal(x1, xp)
 
 
+def test_small_step_without_guidance(small):
+    """unconditional_guidance_scale = 1 (ddim.py:253-254): a single UNet pass, no CFG combine, no guidance rescale."""
+    from camc2v_b200.sampler import DDIMSampler, DenoiserModel
+    from oracle import ddim_oracle
+    cfg, unet, sd, g, inp, cam = small
+    model = DenoiserModel(unet).to(DEV)
+    s = DDIMSampler(model)
+    s.make_schedule(25, "uniform_trailing", 1.0, verbose=False)
+    index = int(g["step_index"])
+    assert int(g["step_t"]) == 599                                   # the timestep y_cond was generated at (make_golden.py)
+    ts = torch.full((1,), int(g["step_t"]), dtype=torch.long, device=DEV)
+    torch.manual_seed(1)
+    noise = torch.randn(inp["x"].shape)
+    cond = {"c_crossattn": [inp["ctx_cond"].to(DEV)], "c_concat": [inp["c_concat"].to(DEV)], "camera_condition": cam}
+    xp, p0 = s.p_sample_ddim(inp["x"].to(DEV), cond, ts, index=index, unconditional_guidance_scale=1.0, fs=inp["fs"].to(DEV),
+                             enable_camera_condition=True, noise=noise.to(DEV), guidance_rescale=0.7)
+    sch = ddim_oracle.ddim_schedule()
+    e = torch.from_numpy(g["y_cond"])                                # the reference's conditional prediction at this timestep
+    xo, po = ddim_oracle.cfg_ddim_update(inp["x"], e, e, noise, float(sch["alphas"][index]), float(sch["alphas_prev"][index]),
+                                         float(sch["sigmas"][index]), float(sch["sqrt_one_minus_alphas"][index]), 1.0, 0.0)
+    assert rel(xp, xo)[0] < TOL_L2 and rel(p0, po)[0] < 2 * TOL_L2
+
+
 def test_sampling_loop_runs_and_is_deterministic(small):
     from camc2v_b200.sampler import DDIMSampler, DenoiserModel
     cfg, unet, sd, g, inp, cam = small
