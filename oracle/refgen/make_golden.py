@@ -370,6 +370,14 @@ POSE_KW = dict(downscale_factor=8, channels=[320, 640], nums_rb=2, cin=384, ksiz
                temporal_position_encoding_max_len=16)
 
 
+# the class's other code paths: 3x3 in_conv / block2 convolutions (ksize 3), three blocks per level with the compression_factor
+# bottleneck, two attention blocks per transformer, no position encoding.  (sk=False cannot run in the reference either unless
+# every in_c == out_c: its skep conv is applied to the in_conv OUTPUT, camera_pose_encoder.py:257-266.)
+POSE_KW_GENERIC = dict(downscale_factor=8, channels=[128, 256], nums_rb=3, cin=384, ksize=3, sk=True, use_conv=False, compression_factor=2,
+                       temporal_attention_nhead=8, attention_block_types=["Temporal_Self", "Temporal_Self"], temporal_position_encoding=False,
+                       temporal_position_encoding_max_len=16)
+
+
 def gen_pose_encoder(check):
     """CameraPoseEncoder (SURVEY f-2) in the shipped configuration (camcontexti2v_256.yaml:125-139) cut to its first two levels
     (head dims 40 and 80), on the Pluecker embedding of a 64 x 64 orbit trajectory.  The reference class itself runs; the two
@@ -401,6 +409,19 @@ def gen_pose_encoder(check):
     if check:
         fo = pose_encoder_oracle.pose_encoder_forward(ref.state_dict(), x, n_levels=2)
         print("    oracle vs reference rel-L2:", [f"{rel_err(a, b)[0]:.3e}" for a, b in zip(fo, feats)])
+    torch.manual_seed(0)
+    ref2 = CameraPoseEncoder(**POSE_KW_GENERIC).eval()
+    synth.fill_module_(ref2, seed=9)
+    with torch.no_grad():
+        feats2 = ref2(x)
+    print("  pose encoder (generic options):", [tuple(f.shape) for f in feats2], [round(float(f.std()), 4) for f in feats2])
+    np.savez_compressed(os.path.join(GOLD, "pose_encoder_generic.npz"), **{f"f{i}": f.numpy() for i, f in enumerate(feats2)},
+                        kwargs=json.dumps(POSE_KW_GENERIC))
+    json.dump({k: list(v.shape) for k, v in ref2.state_dict().items()}, open(os.path.join(GOLD, "state_dict_pose_encoder_generic.json"), "w"),
+              indent=0)
+    if check:
+        fo = pose_encoder_oracle.pose_encoder_forward(ref2.state_dict(), x, n_levels=2, nums_rb=3, n_attn=2)
+        print("    oracle vs reference rel-L2:", [f"{rel_err(a, b)[0]:.3e}" for a, b in zip(fo, feats2)])
 
 
 def gen_camcfg(check):

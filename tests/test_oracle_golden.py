@@ -315,15 +315,21 @@ def pose_state_dict(kw, seed=8):
     return shapes, sd
 
 
-def test_pose_encoder_oracle_matches_reference():
+POSE_CASES = [("pose_encoder_small.npz", "state_dict_pose_encoder.json", 8), ("pose_encoder_generic.npz", "state_dict_pose_encoder_generic.json", 9)]
+
+
+@pytest.mark.parametrize("npz,sdj,seed", POSE_CASES)
+def test_pose_encoder_oracle_matches_reference(npz, sdj, seed):
     """oracle/pose_encoder_oracle.py against the reference's own CameraPoseEncoder (golden made with the restated diffusers stand-ins:
-    parity pinned for the reference file, unpinned for diffusers' Attention / FeedForward - see the oracle's header)."""
+    parity pinned for the reference file, unpinned for diffusers' Attention / FeedForward - see the oracle's header).  Two
+    configurations: the shipped one cut to two levels, and one that takes the class's other branches (3x3 in_conv / block2,
+    compression_factor 2, three blocks per level, two attention blocks, no position encoding)."""
     import json
     from oracle import pose_encoder_oracle
-    g = np.load(os.path.join(GOLD, "pose_encoder_small.npz"))
+    g = np.load(os.path.join(GOLD, npz))
     kw = json.loads(str(g["kwargs"]))
-    shapes, sd = pose_state_dict(kw)
-    assert {k: list(v) for k, v in shapes.items()} == json.load(open(os.path.join(GOLD, "state_dict_pose_encoder.json")))   # drop-in state_dict
+    shapes, sd = pose_state_dict(kw, seed)
+    assert {k: list(v) for k, v in shapes.items()} == json.load(open(os.path.join(GOLD, sdj)))   # drop-in state_dict
     feats = pose_encoder_oracle.pose_encoder_forward(sd, _pose_inputs(), n_levels=len(kw["channels"]), nums_rb=kw["nums_rb"],
                                                      heads=kw["temporal_attention_nhead"], n_attn=len(kw["attention_block_types"]))
     for i, f in enumerate(feats):

@@ -19,12 +19,13 @@ def rel(a, b):
     return float((a - b).norm() / b.norm()), float((a - b).abs().max() / b.abs().max())
 
 
-def test_pose_encoder_vs_reference_golden():
+@pytest.mark.parametrize("npz,seed", [("pose_encoder_small.npz", 8), ("pose_encoder_generic.npz", 9)])
+def test_pose_encoder_vs_reference_golden(npz, seed):
     from camc2v_b200.pose_encoder import CameraPoseEncoder
     from test_oracle_golden import _pose_inputs, pose_state_dict
-    g = np.load(os.path.join(GOLD, "pose_encoder_small.npz"))
+    g = np.load(os.path.join(GOLD, npz))
     kw = json.loads(str(g["kwargs"]))
-    _, sd = pose_state_dict(kw)
+    _, sd = pose_state_dict(kw, seed)
     m = CameraPoseEncoder(**kw)
     m.load_state_dict(sd, strict=True)
     m = m.to(DEV)
