@@ -32,6 +32,13 @@ constexpr int AT_D = 64;
 #ifndef C2V_AT_KV_STAGES
 #define C2V_AT_KV_STAGES 4
 #endif
+// 1: load the packed epipolar mask words of tile j+1 while tile j is processed.  The end-of-round capture
+// (profiles/r01h_ncu_full.txt, SASS page) puts 10 % of the kernel's stall samples on the first use of the mask word: with S
+// double-buffered the wait for S(j) is short, so a load issued right before it is not hidden.  Written at the end of round 1
+// with no GPU time left to measure it: off until it has been A/B-ed (registers: see DESIGN.md section 6).
+#ifndef C2V_AT_MASK_PREFETCH
+#define C2V_AT_MASK_PREFETCH 0
+#endif
 #ifndef C2V_AT_MIN_CTAS
 #define C2V_AT_MIN_CTAS 2
 #endif
@@ -264,14 +271,35 @@ __global__ void __launch_bounds__(AT_THREADS, AT_MIN_CTAS) attn_tc_kernel(const 
         float l_run = 0.f;
         uint8_t* p_row = smem + AT_OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
 
+#if C2V_AT_MASK_PREFETCH
+        // Packed mask words one tile ahead (see the macro's comment): bw_n holds the words of tile j at the top of iteration j.
+        uint32_t bw_n[AT_BN / 32] = {};
+        auto load_mask_words = [&](int jt_, uint32_t (&w)[AT_BN / 32]) {
+#pragma unroll
+            for (int c = 0; c < AT_BN / 32; ++c) w[c] = 0u;
+            if (FAST && p.bitmask && jt_ < n_main) {
+                const uint32_t* mrow_w = p.bitmask + (((size_t)b * gridDim.x + q_tile) * (size_t)(p.lk >> 5) + (size_t)jt_ * (AT_BN / 32)) * AT_BM + r;
+#pragma unroll
+                for (int c = 0; c < AT_BN / 32; ++c) w[c] = __ldg(mrow_w + (size_t)c * AT_BM);
+            }
+        };
+        if (n_act > 0) load_mask_words(tile_list[0], bw_n);
+#endif
+
         for (int j = 0; j < n_act; ++j) {
             const int jt = tile_list[j];              // key tile index (j counts visited tiles: barrier parities)
             uint32_t bw[AT_BN / 32] = {};             // packed mask words of this row for the tile's 32-key chunks
+#if C2V_AT_MASK_PREFETCH
+#pragma unroll
+            for (int c = 0; c < AT_BN / 32; ++c) bw[c] = bw_n[c];
+            if (j + 1 < n_act) load_mask_words(tile_list[j + 1], bw_n);
+#else
             if (FAST && p.bitmask && jt < n_main) {   // issued before the wait for S: the load latency hides behind QK^T
                 const uint32_t* mrow_w = p.bitmask + (((size_t)b * gridDim.x + q_tile) * (size_t)(p.lk >> 5) + (size_t)jt * (AT_BN / 32)) * AT_BM + r;
 #pragma unroll
                 for (int c = 0; c < AT_BN / 32; ++c) bw[c] = __ldg(mrow_w + (size_t)c * AT_BM);
             }
+#endif
             mbar_wait(&s_full[j % AT_S_BUFS], (j / AT_S_BUFS) & 1);
             tc_fence_after();
             const uint32_t t_s = t_s0 + (uint32_t)(j % AT_S_BUFS) * AT_BN;
