@@ -18,6 +18,13 @@
 #include "common.cuh"
 #include "gemm_tc.h"
 
+// 1: the epilogue warps prefetch the bias / row-bias lines of their tile into L1 while they wait for the accumulator.  The ncu
+// captures of the 32x32-level GEMMs put 6-10 % of their stall samples on the first bias add of the epilogue (long scoreboard).
+// Written when the round's GPU time was spent; off until measured (when off the instruction stream is the one of the measured build, up to two renamed uniform registers).
+#ifndef C2V_GEMM_BIAS_PREFETCH
+#define C2V_GEMM_BIAS_PREFETCH 0
+#endif
+
 namespace c2v {
 
 constexpr int BM = 128;
@@ -167,6 +174,18 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 2) gemm_tc_kernel(const _
         const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
         const float* rb = (!part && p.rowbias && row_ok) ? p.rowbias + (size_t)(m / p.rows_per_group) * p.N : nullptr;
         const float* bias = part ? nullptr : p.bias;
+#if C2V_GEMM_BIAS_PREFETCH
+        // While the main loop runs the epilogue warps only wait: pull the tile's bias / row-bias lines into L1 now, so that the
+        // first `f[j] += bias[n]` after the accumulator barrier is an L1 hit instead of a ~600-cycle L2 round trip.  In-bounds
+        // addresses only (the last N tile may be ragged).
+        {
+            const int col = n0 + (int)lane_id() * 32;            // one 128-byte line per lane
+            if (col < p.N && (int)lane_id() * 32 < BN) {
+                if (bias) asm volatile("prefetch.global.L1 [%0];" ::"l"(bias + col));
+                if (rb) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + col));
+            }
+        }
+#endif
         if (EPI_WARPS > 4 && (warp >= 6) && p.epi != EPI_GEGLU) {
             // the second epilogue group only exists for the GEGLU epilogue
         } else if (part && p.cluster_reduce) {
