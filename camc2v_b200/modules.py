@@ -237,12 +237,12 @@ class TimestepBlock(nn.Module):
     pass
 
 
-BATCH_EMB = os.environ.get("C2V_EMB_BATCH", "1") != "0"      # 0: every ResBlock projects the embedding itself (26 launches per pass)
+BATCH_EMB = os.environ.get("C2V_EMB_BATCH", "1") != "0"      # 0: every ResBlock projects the embedding itself (22 launches per pass)
 
 
 class EmbPack:
     """Timestep embedding of a pass plus the emb_layers projections of ALL ResBlocks, computed by one skinny GEMM at the top
-    of UNetModel.forward (26 launches per pass folded into one): block i reads columns [off, off + Cout) of `all`."""
+    of UNetModel.forward (22 launches per pass folded into one): block i reads columns [off, off + Cout) of `all`."""
     __slots__ = ("raw", "all")
 
     def __init__(self, raw: torch.Tensor, all_: torch.Tensor):

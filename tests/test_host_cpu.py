@@ -254,3 +254,23 @@ assert torch.equal(both[0], both[1]), "the two ranks of a pair must stay bit-ide
 print("ok", rank)
 ''' % ROOT
     _run_world(code, 2, 29534)
+
+
+def test_emb_projection_stacking_matches_per_block_packs():
+    """UNetModel stacks the emb_layers projections of all ResBlocks into one skinny GEMM (modules.EmbPack): every block's column
+    slice of the stacked weight / bias must be exactly the block's own pack, and the slices must tile the matrix."""
+    from camc2v_b200 import synth
+    from camc2v_b200.modules import ResBlock, UNetConfig, build_unet
+    unet = build_unet(UNetConfig(model_channels=64, origin_h=128, origin_w=128))
+    synth.fill_module_(unet, seed=0)
+    p = unet.pk()
+    blocks = [m for m in unet.modules() if isinstance(m, ResBlock)]
+    assert len(blocks) == 22
+    off = 0
+    for blk in blocks:
+        o, c = blk._emb_slice
+        assert o == off and c == blk.out_channels
+        bp = blk.pk()
+        assert torch.equal(p["we_all"][o:o + c], bp["we"]) and torch.equal(p["bemb_all"][o:o + c], bp["bemb"])
+        off += c
+    assert p["we_all"].shape == (off, 4 * 64) and p["bemb_all"].shape == (off,)
