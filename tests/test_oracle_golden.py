@@ -335,3 +335,24 @@ def test_pose_encoder_oracle_matches_reference(npz, sdj, seed):
     for i, f in enumerate(feats):
         l2, mx = _rel(f, torch.from_numpy(g[f"f{i}"]))
         assert l2 < 1e-5 and mx < 1e-5, (i, l2, mx)
+
+
+def test_cfg_update_oracle_identities():
+    """Size-independent identities of the CFG + DDIM update (ddim.py:262-346): guidance scale 1 ignores the unconditional branch,
+    camera weight 0 ignores the third prediction, and with eta-noise 0 the step is the deterministic DDIM map whose pred_x0
+    inverts the forward noising exactly."""
+    torch.manual_seed(0)
+    shape = (2, 4, 3, 5, 7)
+    x0, eps, e_u, e_n = (torch.randn(shape) for _ in range(4))
+    a_t, a_prev, sigma = 0.37, 0.52, 0.11
+    x = a_t ** 0.5 * x0 + (1 - a_t) ** 0.5 * eps
+    z = torch.zeros(shape)
+    xp1, p01 = ddim_oracle.cfg_ddim_update(x, eps, e_u, z, a_t, a_prev, sigma, (1 - a_t) ** 0.5, 1.0, 0.0)
+    xp2, p02 = ddim_oracle.cfg_ddim_update(x, eps, eps, z, a_t, a_prev, sigma, (1 - a_t) ** 0.5, 3.5, 0.7)     # e_c == e_u: CFG and rescale are no-ops
+    assert torch.allclose(p01, x0, atol=2e-5) and torch.allclose(p02, x0, atol=2e-5)
+    assert torch.allclose(xp1, xp2, atol=2e-5)
+    ref = a_prev ** 0.5 * x0 + (1 - a_prev - sigma ** 2) ** 0.5 * eps
+    assert torch.allclose(xp1, ref, atol=2e-5)
+    a = ddim_oracle.cfg_ddim_update(x, eps, e_u, z, a_t, a_prev, sigma, (1 - a_t) ** 0.5, 3.5, 0.7)
+    b = ddim_oracle.cfg_ddim_update(x, eps, e_u, z, a_t, a_prev, sigma, (1 - a_t) ** 0.5, 3.5, 0.7, e_cond_nocam=e_n, cam_weight=0.0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
