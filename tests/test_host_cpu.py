@@ -274,3 +274,14 @@ def test_emb_projection_stacking_matches_per_block_packs():
         assert torch.equal(p["we_all"][o:o + c], bp["we"]) and torch.equal(p["bemb_all"][o:o + c], bp["bemb"])
         off += c
     assert p["we_all"].shape == (off, 4 * 64) and p["bemb_all"].shape == (off,)
+
+
+def test_integration_doc_maps_every_abi_symbol():
+    """INTEGRATION.md names the reference interface each exported entry point replaces: no symbol of the header may be missing."""
+    import re
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    hdr = open(os.path.join(root, "include", "camc2v_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(c2v_[a-z0-9_]+)\(", hdr)))
+    assert len(syms) >= 35
+    assert [s for s in syms if s not in doc] == []
