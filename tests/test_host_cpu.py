@@ -285,3 +285,17 @@ def test_integration_doc_maps_every_abi_symbol():
     syms = sorted(set(re.findall(r"\b(c2v_[a-z0-9_]+)\(", hdr)))
     assert len(syms) >= 35
     assert [s for s in syms if s not in doc] == []
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under camc2v_b200/ may import it (bench.py uses it only for the CPU baseline legs)."""
+    import re
+    pkg = os.path.join(os.path.abspath(os.path.join(os.path.dirname(__file__), "..")), "camc2v_b200")
+    bad = []
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "oracle/" in src and f.endswith((".cu", ".cuh", ".h")) and "#include" in src and re.search(r'#include\s+"[^"]*oracle', src):
+                    bad.append(f)
+    assert bad == []
