@@ -2,7 +2,7 @@
 """Benchmark of the CamContextI2V denoising hot path on B200 (driver contract: see the task statement).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W     # CPU arm: the oracle port of the reference on host cores
+    python bench.py --impl reference --steps K --warmup W     # CPU arm: the UNMODIFIED reference (oracle/_ref) on the host cores
 
 Workload (BASELINE.json configs[2]): 25-step DDIM sampling with classifier-free guidance 3.5, guidance
 rescale 0.7, eta 1, `uniform_trailing`, batch 1 video per GPU, 256x256x16f (4x32x32 latents), CamContextI2V
@@ -35,7 +35,6 @@ from camc2v_b200.testing import synth_unet_inputs  # noqa: E402
 
 METRIC = "ddim_steps_per_s"
 UNIT = "DDIM steps/s (256x256, 16 frames, CFG)"
-CPU_SAMPLE_BLOCKS = {"input_blocks.0", "init_attn", "input_blocks.1", "input_blocks.2"}
 
 
 def measured_peaks():
@@ -163,77 +162,63 @@ def pin(t):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm / baseline
-def cpu_sample_setup(cfg: UNetConfig, full: bool = False):
-    """Oracle (CPU port of the reference) on a bounded sample of the workload: the first three input blocks +
-    init_attn of the cond pass at full size — 19.1 % of the cond pass, 10.0 % of a CFG step by algorithmic FLOPs."""
-    sys.path.insert(0, ROOT)
-    import oracle
-    from oracle import camera_oracle
-    from oracle.unet_oracle import UNetOracle
-    from camc2v_b200.config import build_topology
-    from camc2v_b200.modules import build_unet
-
-    topo = build_topology(cfg)
-    with torch.device("meta"):
-        shapes = {k: tuple(v.shape) for k, v in build_unet(cfg).state_dict().items()}
-    need = tuple(n + "." for n in ("input_blocks.0", "input_blocks.1", "input_blocks.2", "init_attn", "time_embed", "fps_embedding"))
-    sd = {k: synth.synth_param(k, s, 0) for k, s in shapes.items() if full or k.startswith(need)}
-    orc = UNetOracle(sd, cfg, fused_epipolar=True)
-    inp = synth_unet_inputs(cfg, 32, 2, "bench0", B=1)
-    K, w2c = synth.synth_camera("pan_yaw", T=cfg.temporal_length, B=1)
-    torch.manual_seed(123)
-    Fm, masks, _ = camera_oracle.camera_condition_masks(K, w2c, torch.zeros(1, dtype=torch.long), resolutions=(8, 4, 2, 1) if full else (1,))
-    cam = {"pluker_embedding_features": inp["pluker"], "sample_locs_dict": masks, "add_type": "add_to_main_branch"}
-    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1)
-    t = torch.full((1,), 599, dtype=torch.long)
-    blocks = None if full else CPU_SAMPLE_BLOCKS
-    frac = (unet_pass_flops(cfg, 1, 32, 845, False, only_blocks=blocks)["total"] / cfg_step_flops(cfg, 1, 32))
-
-    def run():
-        t0 = time.perf_counter()
-        orc.forward(xc, t, inp["ctx_cond"], inp["fs"], cam, max_input_block=None if full else 2)
-        return time.perf_counter() - t0
-
-    return run, frac
+REF_TIMED_BUDGET_S = float(os.environ.get("C2V_REF_BUDGET_S", "240"))    # wall budget of the reference arm's timed region
 
 
-def cpu_baseline(cfg: UNetConfig, repeats: int = 1):
-    torch.set_num_threads(os.cpu_count() or 1)
-    run, frac = cpu_sample_setup(cfg)
-    run()                                   # warm-up (allocator, oneDNN primitive caches)
-    best = min(run() for _ in range(max(1, repeats)))
-    what = "input_blocks.0-2 + init_attn of the cond UNet pass"
-    if best * 5.3 < 25.0:                   # fast host: afford the whole cond pass (52.5 % of a step) as the sample
-        run, frac = cpu_sample_setup(cfg, full=True)
-        best = run()
-        what = "the whole cond UNet pass"
-    return {"value": frac / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle (CPU port of the reference, fp32) on {what} at full size "
-                      f"(B=1, 4x16x32x32 latent, 845-token context, epipolar masks) = {frac * 100:.2f}% of one CFG step's algorithmic "
-                      f"FLOPs; {best:.2f} s per sample, steps/s extrapolated by FLOP share (the unmodified reference measured "
-                      f"57.3 s per full CFG step on 8 cores, BASELINE.md)"}
+def _reference_stepper():
+    """The UNMODIFIED reference's DDIMSampler.p_sample_ddim on this workload, on the host cores (oracle/refgen/ref_bench.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "refgen"))
+    import ref_bench
+    why = ref_bench.reference_available()
+    if why:
+        raise RuntimeError(why)
+    return ref_bench.ReferenceStepper(), ref_bench.SAMPLE_TEXT
+
+
+def cpu_baseline(cfg: UNetConfig):
+    """ONE whole CFG step of the unmodified reference on all host threads (~0.5-1 min): a measurement, no extrapolation."""
+    stepper, text = _reference_stepper()
+    dt = stepper.step()
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": stepper.threads, "kind": "reference",
+            "sample": f"1 step (the first of the 25, no warm-up step), {dt:.1f} s: {text}"}
 
 
 def run_reference_arm(args):
+    """`--impl reference`: whole p_sample_ddim CFG steps of the unmodified reference, CPU, all host threads.  A step costs
+    0.5-1 min of CPU, so the requested --warmup / --steps are honoured up to a wall budget (C2V_REF_BUDGET_S, 240 s of timed
+    region): at most one warm-up step, and as many timed steps as fit.  `steps` / `warmup` in the line are the counts RUN."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = UNetConfig()
-    torch.set_num_threads(os.cpu_count() or 1)
-    run, frac = cpu_sample_setup(cfg)
-    for _ in range(args.warmup):
-        run()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        run()
-    el = time.perf_counter() - t0
-    per = el / args.steps
-    value = frac / per
-    base = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"per step: oracle (CPU port of the reference, fp32, all host threads) on input_blocks.0-2 + init_attn of the cond pass "
-                      f"at full size = {frac * 100:.2f}% of one CFG step's algorithmic FLOPs; steps/s extrapolated by FLOP share"}
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": per / frac * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+    try:
+        stepper, text = _reference_stepper()
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": str(e).splitlines()[0][:200]}), flush=True)
+        return
+    warm = min(max(args.warmup, 0), 1)
+    t_est = None
+    for _ in range(warm):
+        t_est = stepper.step()
+    times = []
+    while len(times) < args.steps:
+        if times or t_est is not None:
+            est = float(np.mean(times)) if times else t_est
+            if times and sum(times) + est > REF_TIMED_BUDGET_S:
+                break
+        times.append(stepper.step())
+    el = float(sum(times))
+    steps = len(times)
+    per = el / steps
+    value = 1.0 / per
+    capped = steps < args.steps or warm < args.warmup
+    note = (f"{steps} timed step(s) after {warm} warm-up step(s) (requested {args.steps} / {args.warmup}; capped by the "
+            f"{REF_TIMED_BUDGET_S:.0f} s timed-region budget, a step takes {per:.1f} s on {stepper.threads} threads)" if capped else
+            f"{steps} timed steps after {warm} warm-up steps")
+    base = {"value": value, "unit": UNIT, "cores": stepper.threads, "kind": "reference", "sample": f"{note}: {text}"}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "steps_requested": args.steps, "warmup_requested": args.warmup, "steps_capped": capped,
+            "ms_per_step": per * 1e3, "per_step_s": [round(t, 2) for t in times], "setup_s": round(stepper.setup_s, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(1, args.gpus), "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)

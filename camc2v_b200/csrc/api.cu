@@ -311,7 +311,13 @@ int c2v_attention(const c2v_attn_desc* d, void* stream) {
         a.tile_map_words = c2v_epipolar_tile_map_words(d->epi_T, d->epi_H, d->epi_W);
     }
     if (d->epi_bitmask && d->epi_F && d->lq % 128 == 0) a.bitmask = d->epi_bitmask;
-    return attn_tc_launch(a, (d->lq + 127) / 128, d->heads, d->bq, (cudaStream_t)stream);
+    // C2V_ATTN_IMPL=tc selects the round-1 two-pass pipeline (attn_tc.cu) for A/B measurements; default: attn_fa.cu
+    static const bool use_tc = [] {
+        const char* e = getenv("C2V_ATTN_IMPL");
+        return e && e[0] == 't';
+    }();
+    if (use_tc) return attn_tc_launch(a, (d->lq + 127) / 128, d->heads, d->bq, (cudaStream_t)stream);
+    return attn_fa_launch(a, (d->lq + 127) / 128, d->heads, d->bq, (cudaStream_t)stream);
 }
 
 int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int heads, void* stream) {

@@ -1,0 +1,590 @@
+// Single-pass flash attention on tcgen05 tensor cores with P kept in tensor memory, head dim 64, 16-bit operands, fp32 softmax.
+//   replaces xformers.ops.memory_efficient_attention (R/lvdm/modules/attention.py:177,189), the einsum softmax path
+//   (attention.py:105-129) and F.scaled_dot_product_attention with the boolean epipolar mask (R/model/modules/epipolar.py:99).
+//
+// Round-2 rebuild of attn_tc.cu's pipeline (profiles/r01h_ncu_full.txt: the round-1 kernel spent ~2050 cycles per 64-key tile
+// against ~256 cycles of MMA; its four softmax warps made two TMEM passes per tile - max + masked-score write-back, then exp - and
+// P went through shared memory with a proxy fence, so softmax(j+1) had to wait for PV(j)).  What changed:
+//   * ONE pass over S: the scores of a tile are read from TMEM once into registers, the mask is applied there (a packed 32-bit
+//     word per 32-key chunk and row; masked scores become -inf in registers, nothing is written back), then max, exp2, sum.
+//   * LAZY rescale (FA-4 style): the running reference maximum of a row is only raised when the tile maximum exceeds it by more
+//     than 2^8; probabilities are then at most 256 (exact in bf16 / fp16 and fp32 sums), and the O accumulator is touched by the
+//     softmax warps only in those rare tiles - the per-tile wait for PV(j-1) is gone from the common path.
+//   * P stays in TENSOR MEMORY: the 16-bit probabilities are stored with tcgen05.st over the first 32 columns of the S buffer
+//     they came from and PV is issued as tcgen05.mma with the A operand from TMEM (no shared-memory P tile, no
+//     fence.proxy.async).  S is double-buffered, so P is too: QK(j+2) overwrites buffer j&1 only after PV(j), which the in-order
+//     tensor pipe guarantees because both are issued by the same thread.
+//   * packed-mask words are fetched one tile ahead.
+// One CTA = 128 query rows of one (batch, head); 64-key tiles (two image rows of a 32x32 latent frame) keep the epipolar tile map
+// fine-grained; two CTAs per SM (TMEM 2 x 64 S/P columns + 64 O columns = 192 -> 256 allocated).
+//
+// Mask forms (all produce the same 32-bit word per (row, 32-key chunk), so outputs are bit-identical across forms):
+//   MODE 0  dense / ragged tails / register-token segment, and the per-sample packed epipolar mask (c2v_epipolar_bitmask)
+//   MODE 1  materialised byte mask in the reference's format, and the exact epipolar predicate on arbitrary grids (rolled loop)
+//   MODE 2  the exact epipolar predicate on square power-of-two grids, evaluated in-kernel from the 3x3 fundamental matrices with
+//           the reference's fp32 operation order (R/model/camcontexti2v.py:229-239)
+#include "attn_tc.h"
+#include "common.cuh"
+
+namespace c2v {
+
+constexpr int FA_BM = 128;   // query rows per CTA
+constexpr int FA_BN = 64;    // keys per tile
+constexpr int FA_D = 64;
+#ifndef C2V_FA_KV_STAGES
+#define C2V_FA_KV_STAGES 4
+#endif
+#ifndef C2V_FA_MIN_CTAS
+#define C2V_FA_MIN_CTAS 2
+#endif
+// 1: one elected lane per softmax warp arrives on p_full (count 4) after __syncwarp; 0: every thread arrives (count 128)
+#ifndef C2V_FA_WARP_ARRIVE
+#define C2V_FA_WARP_ARRIVE 1
+#endif
+// of every 8 probabilities, this many are computed by a polynomial 2^x on the FMA pipe instead of MUFU.EX2 (0 = all on MUFU)
+#ifndef C2V_FA_POLY
+#define C2V_FA_POLY 0
+#endif
+constexpr int FA_KV_STAGES = C2V_FA_KV_STAGES;
+constexpr int FA_THREADS = 192;
+constexpr float FA_TAU = 8.0f;                       // lazy-rescale threshold (log2 units): P <= 2^8
+
+constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;         // 16 KB
+constexpr int FA_K_BYTES = FA_BN * FA_D * 2;         // 8 KB
+constexpr int FA_V_BYTES = FA_BN * FA_D * 2;         // 8 KB
+constexpr int FA_OFF_Q = 0;
+constexpr int FA_OFF_K = FA_OFF_Q + FA_Q_BYTES;
+constexpr int FA_OFF_V = FA_OFF_K + FA_KV_STAGES * FA_K_BYTES;
+constexpr int FA_OFF_BAR = FA_OFF_V + FA_KV_STAGES * FA_V_BYTES;
+constexpr int FA_OFF_LIST = FA_OFF_BAR + 256;
+constexpr int FA_MAX_TILES = 1024;
+constexpr int FA_SMEM = FA_OFF_LIST + FA_MAX_TILES * 2;
+
+constexpr uint32_t FA_TM_S = 0;                      // S / P buffers: 2 x 64 columns (P = first 32 columns of its S buffer)
+constexpr uint32_t FA_TM_O = 2 * FA_BN;              // O accumulator: 64 columns
+constexpr uint32_t FA_TMEM_COLS = 256;
+
+constexpr uint32_t FA_NEG_INF = 0xff800000u;
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (P, 16-bit, K-major: lane = row, one 32-bit column = two consecutive k) is read
+// straight from tensor memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+struct FaLine {
+    float l0, l1, l2;
+};
+// Normalised epipolar line of query pixel (xi, yi) in frame t2 (camcontexti2v.py:229-236); same arithmetic as attn_tc.cu / epipolar.cu
+__device__ __forceinline__ FaLine fa_epi_line(const float* __restrict__ f, float xi, float yi) {
+    float a0 = __fmaf_rn(f[2], 1.0f, __fmaf_rn(f[1], yi, __fmul_rn(f[0], xi)));
+    float a1 = __fmaf_rn(f[5], 1.0f, __fmaf_rn(f[4], yi, __fmul_rn(f[3], xi)));
+    float a2 = __fmaf_rn(f[8], 1.0f, __fmaf_rn(f[7], yi, __fmul_rn(f[6], xi)));
+    const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
+    FaLine l;
+    l.l0 = __fdiv_rn(a0, nrm);
+    l.l1 = __fdiv_rn(a1, nrm);
+    l.l2 = __fdiv_rn(a2, nrm);
+    return l;
+}
+
+// max of 32 scores held as raw bits: four independent chains of 3-input maxima (FMNMX3)
+__device__ __forceinline__ float fa_max32(const uint32_t (&v)[32]) {
+    float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        a0 = fmaxf(a0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        a1 = fmaxf(a1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+        a2 = fmaxf(a2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+        a3 = fmaxf(a3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+    }
+    return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+}
+
+// 2^x for x <= 8 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-4 minimax polynomial of
+// 2^f (max rel. error 4e-6, far below the 2^-11 / 2^-8 rounding of the 16-bit P operand), exponent inserted by an integer add.
+// x is clamped at -126 so that the exponent field cannot wrap; callers zero masked (-inf) entries themselves.
+__device__ __forceinline__ float fa_exp2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = __fadd_rn(x, 12582912.0f);                 // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+    const float f = __fadd_rn(x, -__fadd_rn(t, -12582912.0f));
+    float p = __fmaf_rn(9.6181291076e-3f, f, 5.5504108665e-2f);
+    p = __fmaf_rn(p, f, 2.4022650696e-1f);
+    p = __fmaf_rn(p, f, 6.9314718056e-1f);
+    p = __fmaf_rn(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int LOGW, int D, int MODE>
+__global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(const __grid_constant__ AttnKernelArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;     // [FA_KV_STAGES <= 4]
+    uint64_t* kv_empty = bars + 5;    // [FA_KV_STAGES <= 4]
+    uint64_t* s_full = bars + 9;      // [2]  S(j) is in TMEM buffer j & 1
+    uint64_t* p_full = bars + 11;     // [2]  P(j) has been stored over S(j)
+    uint64_t* pv_done = bars + 13;    // one phase per PV(j)
+    uint64_t* o_final = bars + 14;    // the last PV
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+    int* n_act_s = reinterpret_cast<int*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5;
+    // CTA -> (query tile, head); with an epipolar tile map the CTAs are issued heaviest query tile first (see attn_tc.cu)
+    const int b = blockIdx.z;
+    int q_tile = blockIdx.x, head = blockIdx.y;
+    if (p.tile_map) {
+        const int lin = blockIdx.x + gridDim.x * blockIdx.y;
+        head = lin % gridDim.y;
+        q_tile = (int)p.tile_map[((size_t)b * gridDim.x + lin / gridDim.y) * p.tile_map_words + (p.tile_map_words - 1)];
+    }
+    const int q0 = q_tile * FA_BM;
+    const int bkv = b / p.kv_div;
+    const int n_main = (p.lk + FA_BN - 1) / FA_BN;
+    const int n_tiles = n_main + (p.lk2 > 0 ? 1 : 0);       // last tile = register-token segment
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) {
+            printf("camc2v_b200: attention smem base not 1024B aligned\n");
+            __trap();
+        }
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        if (p.lk2 > 0) {
+            tma_prefetch_desc(&p.tmK2);
+            tma_prefetch_desc(&p.tmV2);
+        }
+        mbar_init(q_full, 1);
+        for (int s = 0; s < FA_KV_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], C2V_FA_WARP_ARRIVE ? 4 : 128);
+        }
+        mbar_init(pv_done, 1);
+        mbar_init(o_final, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, FA_TMEM_COLS);
+        tmem_relinquish();
+    }
+    // key tiles this query tile visits (epipolar tile map: tiles that cannot contain an unmasked pair are never loaded)
+    uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + FA_OFF_LIST);
+    if (warp == 2) {
+        const uint32_t* map = p.tile_map ? p.tile_map + ((size_t)b * gridDim.x + q_tile) * p.tile_map_words : nullptr;
+        int cnt = 0;
+        for (int j0 = 0; j0 < n_tiles; j0 += 32) {
+            const int j = j0 + lane_id();
+            bool act = j < n_tiles;
+            if (act && map && j < n_main) act = (map[j >> 5] >> (j & 31)) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, act);
+            if (act) tile_list[cnt + __popc(bal & ((1u << lane_id()) - 1u))] = (uint16_t)j;
+            cnt += __popc(bal);
+        }
+        if (lane_id() == 0) *n_act_s = cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int n_act = *n_act_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (n_act > 0 && elect_one()) {
+            mbar_expect_tx(q_full, FA_Q_BYTES);
+            tma_load_3d(smem + FA_OFF_Q, &p.tmQ, q_full, head * FA_D, q0, b);
+            for (int it = 0; it < n_act; ++it) {
+                const int j = tile_list[it];
+                const int s = it % FA_KV_STAGES;
+                const uint32_t ph = (it / FA_KV_STAGES) & 1;
+                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_expect_tx(&kv_full[s], FA_K_BYTES + FA_V_BYTES);
+                if (j < n_main) {
+                    tma_load_3d(smem + FA_OFF_K + s * FA_K_BYTES, &p.tmK, &kv_full[s], head * FA_D, j * FA_BN, bkv);
+                    tma_load_3d(smem + FA_OFF_V + s * FA_V_BYTES, &p.tmV, &kv_full[s], head * FA_D, j * FA_BN, bkv);
+                } else {
+                    tma_load_3d(smem + FA_OFF_K + s * FA_K_BYTES, &p.tmK2, &kv_full[s], head * FA_D, 0, 0);
+                    tma_load_3d(smem + FA_OFF_V + s * FA_V_BYTES, &p.tmV2, &kv_full[s], head * FA_D, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (n_act > 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_bf16(FA_BM, FA_BN, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(FA_BM, FA_D, 0, 1);   // A = P from TMEM (K-major), B = V is MN-major
+            const uint32_t q_addr = smem_u32(smem + FA_OFF_Q);
+            auto issue_qk = [&](int j) {                  // S(j) -> TMEM buffer j & 1
+                const int s = j % FA_KV_STAGES;
+                mbar_wait(&kv_full[s], (j / FA_KV_STAGES) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t qd = umma_desc_sw128(q_addr);
+                    const uint64_t kd = umma_desc_sw128(smem_u32(smem + FA_OFF_K + s * FA_K_BYTES));
+#pragma unroll
+                    for (int k = 0; k < FA_D / 16; ++k)
+                        umma_bf16_ss(tmem_base + FA_TM_S + (uint32_t)(j & 1) * FA_BN, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+                    umma_commit(&s_full[j & 1]);
+                }
+                __syncwarp();
+            };
+            mbar_wait(q_full, 0);
+            issue_qk(0);
+            if (n_act > 1) issue_qk(1);
+            for (int j = 0; j < n_act; ++j) {
+                const int s = j % FA_KV_STAGES;
+                mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t v_addr = smem_u32(smem + FA_OFF_V + s * FA_V_BYTES);
+                    const uint32_t p_tmem = tmem_base + FA_TM_S + (uint32_t)(j & 1) * FA_BN;
+#pragma unroll
+                    for (int ks = 0; ks < FA_BN / 16; ++ks) {
+                        const uint64_t vd = umma_desc_sw128(v_addr + ks * 16 * 128);
+                        umma_bf16_ts(tmem_base + FA_TM_O, p_tmem + ks * 8, vd, idesc_pv, (j | ks) != 0);
+                    }
+                    umma_commit(&kv_empty[s]);
+                    umma_commit(pv_done);
+                    if (j == n_act - 1) umma_commit(o_final);
+                }
+                __syncwarp();
+                // the tensor pipe executes this thread's MMAs in issue order: QK(j+2) may overwrite buffer j & 1 (= P(j)) now
+                if (j + 2 < n_act) issue_qk(j + 2);
+            }
+        }
+    } else {
+        // ===================== softmax / rescale / epilogue (warps 2..5) =====================
+        const int lg = warp & 3;
+        const int r = lg * 32 + lane_id();
+        const int qi = q0 + r;                                     // query index inside the batch
+        const uint32_t t_s0 = tmem_base + FA_TM_S + ((uint32_t)(lg * 32) << 16);
+        const uint32_t t_o = tmem_base + FA_TM_O + ((uint32_t)(lg * 32) << 16);
+        const bool epi = p.epi_F != nullptr;
+        const bool use_words = MODE == 0 && epi && p.bitmask != nullptr;
+        const unsigned char* mrow = (MODE == 1 && p.mask) ? p.mask + (size_t)b * p.mask_bstride + (size_t)min(qi, p.lq - 1) * p.lk : nullptr;
+        // epipolar query geometry (MODE 1 / 2 only)
+        const int HW = p.epi_H * p.epi_W;
+        float xi = 0.f, yi = 0.f;
+        const float* Frow = nullptr;
+        if (MODE != 0 && epi) {
+            const int qc = min(qi, p.lq - 1);
+            const int t1 = qc / HW, pix = qc % HW;
+            xi = __fadd_rn(__fmul_rn((float)(pix % p.epi_W), (float)p.epi_d), p.epi_off);
+            yi = __fadd_rn(__fmul_rn((float)(pix / p.epi_W), (float)p.epi_d), p.epi_off);
+            Frow = p.epi_F + ((size_t)b * p.epi_T + t1) * p.epi_T * 9;
+        }
+        int cur_t2 = -1;
+        FaLine line = {0.f, 0.f, 0.f};
+        float thr_m = 0.f;
+        float l0x[MODE == 2 ? (1 << LOGW) : 1];
+
+        float m_ref = -INFINITY;   // reference maximum of the exponentials (log2 domain), raised lazily
+        float l_run = 0.f;
+
+        const uint32_t* wbase = use_words ? p.bitmask + ((size_t)b * gridDim.x + q_tile) * (size_t)(p.lk >> 5) * FA_BM + r : nullptr;
+        uint32_t bw_n[2] = {0u, 0u};                       // packed mask words of the NEXT tile (fetched one tile ahead)
+        auto fetch_words = [&](int jt_, uint32_t (&w)[2]) {
+            if (jt_ < n_main) {
+                const uint32_t* q = wbase + (size_t)jt_ * 2 * FA_BM;
+                w[0] = __ldg(q);
+                w[1] = __ldg(q + FA_BM);
+            }
+        };
+        if (use_words && n_act > 0) fetch_words(tile_list[0], bw_n);
+
+        for (int j = 0; j < n_act; ++j) {
+            const int jt = tile_list[j];
+            const bool main_seg = jt < n_main;
+            const int klim = main_seg ? p.lk : p.lk2;
+            const int tile_key0 = main_seg ? jt * FA_BN : 0;
+            // ---- mask words of this row for the tile's two 32-key chunks: bit i = key (chunk base + i) is attended ----
+            uint32_t bw[2];
+            if (use_words && main_seg) {
+                bw[0] = bw_n[0];
+                bw[1] = bw_n[1];
+            } else if (MODE == 2 && epi && main_seg) {
+                constexpr int W = 1 << (MODE == 2 ? LOGW : 5);
+                constexpr int RPC = 32 / W;
+                constexpr float DF = (float)D, OFFC = (float)D * 0.5f - 0.5f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int key0 = tile_key0 + c * 32;
+                    const int t2 = key0 >> (2 * LOGW);
+                    if (t2 != cur_t2) {                     // warp-uniform: once per key frame
+                        cur_t2 = t2;
+                        line = fa_epi_line(Frow + t2 * 9, xi, yi);
+                        const float cmax = (float)(W - 1) * DF + OFFC;
+                        thr_m = p.epi_thr + 1e-6f + 4e-7f * (fabsf(line.l0) * cmax + fabsf(line.l1) * cmax + fabsf(line.l2));
+#pragma unroll
+                        for (int x = 0; x < W; ++x) l0x[x] = __fmul_rn(line.l0, (float)x * DF + OFFC);
+                    }
+                    const int py0 = (key0 & (W * W - 1)) >> LOGW;
+                    float yr[RPC];
+                    bool maybe = false;
+#pragma unroll
+                    for (int rr = 0; rr < RPC; ++rr) {
+                        yr[rr] = (float)(py0 + rr) * DF + OFFC;
+                        const float w0 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, OFFC)), line.l2);
+                        const float w1 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, (float)(W - 1) * DF + OFFC)), line.l2);
+                        maybe |= !((w0 > thr_m && w1 > thr_m) || (w0 < -thr_m && w1 < -thr_m));
+                    }
+                    uint32_t word = 0;
+                    if (maybe) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float wv = __fadd_rn(__fmaf_rn(line.l1, yr[i >> LOGW], l0x[i & (W - 1)]), line.l2);
+                            word |= (fabsf(wv) < p.epi_thr ? 1u : 0u) << i;
+                        }
+                    }
+                    bw[c] = word;
+                }
+            } else if (MODE == 1 && main_seg && mrow) {
+                // materialised byte mask (reference format, bool / uint8 [B, lq, lk]): 32 bytes -> one word
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int key0 = tile_key0 + c * 32;
+                    uint32_t word = 0;
+                    if (key0 + 32 <= p.lk && (p.lk & 15) == 0) {
+                        const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + key0);
+                        const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + key0 + 16);
+                        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                        for (int w8 = 0; w8 < 8; ++w8)      // non-zero byte -> bit: 0xFF per byte, top bits gathered by a multiply
+                            word |= (((((__vcmpne4(mw[w8], 0u) >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * w8);
+                    } else {
+#pragma unroll 1
+                        for (int i = 0; i < 32; ++i) {
+                            const int key = key0 + i;
+                            word |= ((key < klim && mrow[key] != 0) ? 1u : 0u) << i;
+                        }
+                    }
+                    bw[c] = word;
+                }
+            } else if (MODE == 1 && main_seg && epi) {
+                // exact predicate on an arbitrary grid (non power-of-two, or a chunk spanning several frames): rolled loop
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int key0 = tile_key0 + c * 32;
+                    uint32_t word = 0;
+#pragma unroll 1
+                    for (int i = 0; i < 32; ++i) {
+                        const int key = key0 + i;
+                        bool ok = key < klim;
+                        if (ok) {
+                            const int t2 = key / HW;
+                            if (t2 != cur_t2) {
+                                cur_t2 = t2;
+                                line = fa_epi_line(Frow + t2 * 9, xi, yi);
+                            }
+                            const int pj = key - t2 * HW;
+                            const float xj = __fadd_rn(__fmul_rn((float)(pj % p.epi_W), (float)p.epi_d), p.epi_off);
+                            const float yj = __fadd_rn(__fmul_rn((float)(pj / p.epi_W), (float)p.epi_d), p.epi_off);
+                            const float dist = fabsf(__fadd_rn(__fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj)), line.l2));
+                            ok = dist < p.epi_thr;
+                        }
+                        word |= (ok ? 1u : 0u) << i;
+                    }
+                    bw[c] = word;
+                }
+            } else {
+                // dense keys (and the never-masked register-token segment): everything below klim
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int nv = klim - (tile_key0 + c * 32);
+                    bw[c] = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+                }
+            }
+            if (use_words && j + 1 < n_act) fetch_words(tile_list[j + 1], bw_n);
+            // rows past lq (ragged last query tile) run like every other row; their output is never stored
+            const bool act0 = __any_sync(0xffffffffu, bw[0] != 0u);
+            const bool act1 = __any_sync(0xffffffffu, bw[1] != 0u);
+            const bool full0 = __all_sync(0xffffffffu, bw[0] == 0xffffffffu);
+            const bool full1 = __all_sync(0xffffffffu, bw[1] == 0xffffffffu);
+
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_s = t_s0 + (uint32_t)(j & 1) * FA_BN;
+            uint32_t v0[32], v1[32];
+            if (act0) tmem_ld32(t_s, v0);
+            if (act1) tmem_ld32(t_s + 32, v1);
+            tmem_ld_wait();
+            float mx = -INFINITY;
+            if (act0) {
+                if (!full0) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v0[i] = (bw[0] >> i) & 1u ? v0[i] : FA_NEG_INF;
+                }
+                mx = fa_max32(v0);
+            }
+            if (act1) {
+                if (!full1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v1[i] = (bw[1] >> i) & 1u ? v1[i] : FA_NEG_INF;
+                }
+                mx = fmaxf(mx, fa_max32(v1));
+            }
+            // ---- lazy rescale: raise the reference maximum only when this tile exceeds it by more than 2^TAU ----
+            const float mt = mx * p.scale_log2;                       // scale > 0; -inf stays -inf
+            if (__any_sync(0xffffffffu, mt > m_ref + FA_TAU)) {       // first valid tile of a row: m_ref = -inf -> true
+                const float m_new = fmaxf(m_ref, mt);
+                const float alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_new);
+                l_run *= alpha;
+                m_ref = m_new;
+                if (j > 0) {                                          // O holds PV(0..j-1): wait for PV(j-1), rescale in place
+                    mbar_wait(pv_done, (j - 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(t_o + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(t_o + c * 32, o);
+                    }
+                }
+            }
+            const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+            // ---- probabilities -> 16-bit pairs -> TMEM (over the S columns just consumed) ----
+            float2 l2 = make_float2(0.f, 0.f);
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
+            auto probs16 = [&](const uint32_t (&v)[32], uint32_t (&w)[16]) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float2 x = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+                    float2 e;
+                    constexpr int NP = C2V_FA_POLY;                   // elements per 8 on the FMA pipe
+                    const int pos = (2 * i) & 7;                      // position of the pair's first element in its group of 8
+                    const bool px = pos < NP, py = pos + 1 < NP;
+                    e.x = px ? (v[2 * i] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.x)) : fast_exp2(x.x);
+                    e.y = py ? (v[2 * i + 1] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.y)) : fast_exp2(x.y);
+                    l2 = fadd2(l2, e);
+                    w[i] = pack_bf16(e.x, e.y);
+                }
+            };
+            const uint32_t t_p = t_s;                                 // P(j): columns [0, 32) of S buffer j & 1
+            {
+                uint32_t w[16];
+                if (act0) {
+                    probs16(v0, w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = 0u;
+                }
+                tmem_st16(t_p, w);
+            }
+            {
+                uint32_t w[16];
+                if (act1) {
+                    probs16(v1, w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = 0u;
+                }
+                tmem_st16(t_p + 16, w);
+            }
+            l_run += l2.x + l2.y;
+            tmem_st_wait();
+            tc_fence_before();
+#if C2V_FA_WARP_ARRIVE
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&p_full[j & 1]);
+#else
+            mbar_arrive(&p_full[j & 1]);
+#endif
+        }
+        // ---- epilogue: O / l -> 16-bit -> global ----
+        if (n_act > 0) {
+            mbar_wait(o_final, 0);
+            tc_fence_after();
+        }
+        const float inv = (l_run > 1e-30f && n_act > 0) ? p.out_scale / l_run : 0.f;
+        const bool row_ok = qi < p.lq;
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)b * p.o_bstride + (size_t)qi * p.ldo + head * FA_D;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            if (n_act > 0) {
+                tmem_ld32(t_o + c * 32, o);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = 0u;
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = inv != 0.f ? __uint_as_float(o[i + e]) * inv : 0.f;
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32 + i);
+                    if (p.accumulate) {
+                        const uint4 prev = *dst;
+                        const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            f[2 * e] += __low2float(ph[e]);
+                            f[2 * e + 1] += __high2float(ph[e]);
+                        }
+                    }
+                    *dst = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, FA_TMEM_COLS);
+    }
+}
+
+template <int LOGW, int D, int MODE>
+static int launch_fa(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        C2V_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel<LOGW, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        attr_set = true;
+    }
+    attn_fa_kernel<LOGW, D, MODE><<<dim3(q_tiles, heads, batch), FA_THREADS, FA_SMEM, st>>>(a);
+    C2V_CHECK_CUDA(cudaGetLastError());
+    return OK;
+}
+
+int attn_fa_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
+    if ((a.lk + FA_BN - 1) / FA_BN + (a.lk2 > 0 ? 1 : 0) > FA_MAX_TILES || a.lk2 > FA_BN) return ERR_UNSUPPORTED;
+    if (!a.epi_F && !a.mask) return launch_fa<0, 1, 0>(a, q_tiles, heads, batch, st);                 // dense
+    if (a.epi_F && a.bitmask && a.lk % FA_BN == 0) return launch_fa<0, 1, 0>(a, q_tiles, heads, batch, st);   // per-sample packed mask
+    AttnKernelArgs g = a;
+    g.bitmask = nullptr;
+    if (a.epi_F && a.epi_H == a.epi_W && a.lk % FA_BN == 0) {
+        const int w = a.epi_W, d = a.epi_d;
+        if (w == 32 && d == 8) return launch_fa<5, 8, 2>(g, q_tiles, heads, batch, st);
+        if (w == 16 && d == 16) return launch_fa<4, 16, 2>(g, q_tiles, heads, batch, st);
+        if (w == 8 && d == 32) return launch_fa<3, 32, 2>(g, q_tiles, heads, batch, st);
+        if (w == 16 && d == 8) return launch_fa<4, 8, 2>(g, q_tiles, heads, batch, st);
+        if (w == 8 && d == 16) return launch_fa<3, 16, 2>(g, q_tiles, heads, batch, st);
+    }
+    g.tile_map = nullptr;                     // the tile map is defined for the power-of-two grids only
+    return launch_fa<0, 1, 1>(g, q_tiles, heads, batch, st);
+}
+
+}  // namespace c2v

@@ -577,19 +577,52 @@ __global__ void __launch_bounds__(128) epi_bitmask_kernel(const float* __restric
     }
 }
 
+// Any grid (e.g. the 4x4 level at d = 64, where a 32-key chunk spans two frames): one thread per (query, 32-key chunk), the
+// predicate in the general form of the reference (pixel centres x*d + d/2 - 0.5, camcontexti2v.py:213-239).  Once per sample.
+__global__ void __launch_bounds__(128) epi_bitmask_generic_kernel(const float* __restrict__ Fm, unsigned int* __restrict__ out, int T, int H, int W,
+                                                                  int d, float thr, float off) {
+    const int HW = H * W, L = T * HW;
+    const int c = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
+    const int r = threadIdx.x;
+    const int qi = qt * AT_BM + r;                   // L % 128 == 0 (checked by the launcher)
+    const int t1 = qi / HW, pix = qi % HW;
+    const float xi = __fadd_rn(__fmul_rn((float)(pix % W), (float)d), off), yi = __fadd_rn(__fmul_rn((float)(pix / W), (float)d), off);
+    const float* Frow = Fm + ((size_t)b * T + t1) * T * 9;
+    int cur_t2 = -1;
+    EpiLine line = {0.f, 0.f, 0.f};
+    unsigned int word = 0;
+    for (int i = 0; i < 32; ++i) {
+        const int key = c * 32 + i;
+        if (key >= L) break;
+        const int t2 = key / HW;
+        if (t2 != cur_t2) {
+            cur_t2 = t2;
+            line = epi_line(Frow + t2 * 9, xi, yi);
+        }
+        const int pj = key - t2 * HW;
+        const float xj = __fadd_rn(__fmul_rn((float)(pj % W), (float)d), off);
+        const float yj = __fadd_rn(__fmul_rn((float)(pj / W), (float)d), off);
+        const float dist = fabsf(__fadd_rn(__fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj)), line.l2));
+        word |= (dist < thr ? 1u : 0u) << i;
+    }
+    out[(((size_t)b * gridDim.y + qt) * gridDim.x + c) * AT_BM + r] = word;
+}
+
 int epi_bitmask_launch(const float* F, unsigned int* out, int B, int T, int H, int W, int d, cudaStream_t st) {
-    if (H != W) return ERR_UNSUPPORTED;
     const int L = T * H * W;
-    if (L % AT_BM != 0 || B > 65535) return ERR_UNSUPPORTED;
+    if (L % AT_BM != 0 || L % 32 != 0 || B > 65535) return ERR_UNSUPPORTED;
     const float thr = (float)((double)d * sqrt(2.0) / 2.0);
     dim3 grid(T, L / AT_BM, B);
 #define C2V_BM(LW, DD) epi_bitmask_kernel<LW, DD><<<grid, 128, 0, st>>>(F, out, T, thr)
-    if (W == 32 && d == 8) C2V_BM(5, 8);
-    else if (W == 16 && d == 16) C2V_BM(4, 16);
-    else if (W == 8 && d == 32) C2V_BM(3, 32);
-    else if (W == 16 && d == 8) C2V_BM(4, 8);
-    else if (W == 8 && d == 16) C2V_BM(3, 16);
-    else return ERR_UNSUPPORTED;
+    if (H == W && W == 32 && d == 8) C2V_BM(5, 8);
+    else if (H == W && W == 16 && d == 16) C2V_BM(4, 16);
+    else if (H == W && W == 8 && d == 32) C2V_BM(3, 32);
+    else if (H == W && W == 16 && d == 8) C2V_BM(4, 8);
+    else if (H == W && W == 8 && d == 16) C2V_BM(3, 16);
+    else {
+        if (L / AT_BM > 65535) return ERR_UNSUPPORTED;
+        epi_bitmask_generic_kernel<<<dim3(L / 32, L / AT_BM, B), 128, 0, st>>>(F, out, T, H, W, d, thr, (float)d / 2.0f - 0.5f);
+    }
 #undef C2V_BM
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;

@@ -31,6 +31,8 @@ struct AttnKernelArgs {
 };
 
 int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st);
+// attn_fa.cu: the round-2 pipeline (single-pass softmax, lazy rescale, P kept in tensor memory, PV as a TMEM-operand MMA)
+int attn_fa_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st);
 // attn_small.cu: dense attention with lk <= 256 on warp-level tensor cores (all of K / V resident in shared memory)
 int attn_small_launch(const void* q, const void* k, const void* v, void* out, int bq, int lq, int lk, int heads, int kv_div, int ldq, int ldk,
                       int ldv, int ldo, long long q_bstride, long long k_bstride, long long v_bstride, long long o_bstride, float scale_log2,

@@ -123,6 +123,24 @@ class _Prepared(nn.Module):
         return {}
 
 
+class _RefBindable:
+    """The reference's model classes re-bind `forward` / `_forward` of UNet sub-modules BY CLASS NAME when they are constructed
+    (camcontexti2v.py:111-170, cami2v.py, cameractrl.py, motionctrl.py: `setattr(module, 'forward', new_forward_for_...)`).
+    Those python forwards are what THIS package replaces: the forwards of the classes below already implement the
+    camera-conditioned behaviour of modified_forwards.py on the CUDA path.  So that `unet_config.target:
+    camc2v_b200.modules.UNetModel` is a drop-in for the UNMODIFIED reference constructor, an attempt to overwrite one of these
+    forwards with a plain function is declined (and recorded in `_declined_rebinds` for inspection)."""
+
+    _GUARDED = ("forward", "_forward")
+
+    def __setattr__(self, name, value):
+        if name in self._GUARDED and callable(value) and not isinstance(value, nn.Module):
+            fn = getattr(value, "__func__", value)
+            self.__dict__.setdefault("_declined_rebinds", []).append(getattr(fn, "__name__", repr(fn)))
+            return
+        super().__setattr__(name, value)
+
+
 def _conv3x3_pack(conv: nn.Conv2d, pad_cin: int = 0):
     w = conv.weight.detach()
     cout, cin = w.shape[0], w.shape[1]
@@ -318,6 +336,52 @@ class ResBlock(_Prepared, TimestepBlock):
 
 
 # =================================================================================================
+# derived-state caches: eviction that can never pull a buffer from under a captured CUDA graph
+# =================================================================================================
+_PINNED: Dict[int, int] = {}            # id(cache entry list) -> pin count; a pinned entry is never evicted
+
+
+def _evict(cache: dict, limit: int) -> None:
+    """Drop the oldest unpinned entries once `cache` holds more than `limit`.  (The previous wholesale `.clear()` could free
+    tile maps / packed masks / projected K/V that a captured graph still points at; replays then read recycled memory.)"""
+    if len(cache) <= limit:
+        return
+    for k in list(cache.keys()):
+        if len(cache) <= limit:
+            break
+        if id(cache[k]) not in _PINNED:
+            del cache[k]
+
+
+def _all_cache_entries(model: Optional[nn.Module]):
+    for cache in (_CONTEXT_CACHE, _TILEMAP_CACHE, _BITMASK_CACHE, _PLUKER_CACHE):
+        yield from cache.values()
+    if model is not None:
+        for m in model.modules():
+            c = m.__dict__.get("_ctx_cache")
+            if c:
+                yield from c.values()
+
+
+def pin_caches(model: Optional[nn.Module] = None) -> list:
+    """Called by the sampler right after a CUDA-graph capture: every cache entry alive now may be referenced by pointer from
+    the captured kernels, so it is pinned (kept, and still refreshed in place) until `unpin_caches(token)`."""
+    token = list(_all_cache_entries(model))          # holding the entry lists also keeps their buffers alive
+    for e in token:
+        _PINNED[id(e)] = _PINNED.get(id(e), 0) + 1
+    return token
+
+
+def unpin_caches(token: Optional[list]) -> None:
+    for e in token or ():
+        n = _PINNED.get(id(e), 0) - 1
+        if n <= 0:
+            _PINNED.pop(id(e), None)
+        else:
+            _PINNED[id(e)] = n
+
+
+# =================================================================================================
 # attention blocks
 # =================================================================================================
 class GEGLU(nn.Module):
@@ -417,8 +481,7 @@ class CrossAttention(_Prepared):
         key = (slot, src.data_ptr(), tuple(src.shape))
         ent = cache.get(key)
         if ent is None:
-            if len(cache) > 8:
-                cache.clear()
+            _evict(cache, 8)
             ent = cache[key] = [ctx.gen, ops.linear(src, w, out_dtype=BF16), ctx, w, slot]
         elif ent[0] != ctx.gen:
             ent[0] = ctx.gen
@@ -473,8 +536,10 @@ def make_context_pack(context: torch.Tensor, T: int, text_len: int = 77, per_fra
     if ent is not None and ent[0] == context._version:
         return ent[1]
     pack = _make_context_pack(context, T, text_len, per_frame, ent[1] if ent is not None else None)
-    if len(_CONTEXT_CACHE) > 16:
-        _CONTEXT_CACHE.clear()
+    if ent is not None:                                  # same buffer refilled in place: keep the (possibly pinned) entry object
+        ent[0], ent[1] = context._version, pack
+        return pack
+    _evict(_CONTEXT_CACHE, 16)
     _CONTEXT_CACHE[key] = [context._version, pack, context]
     return pack
 
@@ -505,6 +570,9 @@ def _cast_into(src_f32: torch.Tensor, old: Optional[torch.Tensor]):
 
 
 def _make_context_pack(context: torch.Tensor, T: int, text_len: int, per_frame: Optional[bool], old: Optional[ContextPack]) -> ContextPack:
+    """With `old` (same source buffer refilled in place) the token matrices are re-cast INTO the old pack's buffers and the SAME
+    pack object is returned with `gen` bumped: every layer's `_ctx_cache` entry holds that object, so `refresh_context_caches`
+    sees the new generation and re-projects K/V into the buffers a captured graph points at."""
     B, L, D = context.shape
     if per_frame is None:
         per_frame = (L == text_len + T * 16)
@@ -519,7 +587,10 @@ def _make_context_pack(context: torch.Tensor, T: int, text_len: int, per_frame: 
         else:
             ilen, idiv = L - text_len, T
             image = _cast_into(img.view(B * ilen, D), old.image if old is not None else None)
-    return ContextPack(text, T, text_len, image, idiv, ilen, (old.gen + 1) if old is not None else 0)
+    if old is not None:
+        old.gen += 1
+        return old
+    return ContextPack(text, T, text_len, image, idiv, ilen, 0)
 
 
 class EpipolarCrossAttention(_Prepared):
@@ -601,6 +672,20 @@ class Epipolar(nn.Module):
         nn.init.zeros_(self.epipolar_attn.to_out[0].weight)
         nn.init.zeros_(self.epipolar_attn.to_out[0].bias)
 
+    @classmethod
+    def adopt(cls, ref: nn.Module) -> "Epipolar":
+        """Build this class from an instance of the reference's `Epipolar` (R/model/modules/epipolar.py:105-126), which the
+        reference's constructors inject with `add_module('epipolar', Epipolar(...))` (camcontexti2v.py:158-166): same
+        hyper-parameters, same parameter names / shapes, parameter values copied."""
+        attn = ref.epipolar_attn
+        new = cls(query_dim=attn.to_q.in_features, context_dim=attn.to_k.in_features, heads=ref.num_heads, origin_h=ref.origin_h,
+                  origin_w=ref.origin_w, is_3d_full_attn=ref.is_3d_full_attn, num_register_tokens=attn.num_register_tokens,
+                  compression_factor=getattr(ref, "compression_factor", 1), only_on_cond_frame=getattr(ref, "only_on_cond_frame", False))
+        new.load_state_dict(ref.state_dict(), strict=True)
+        for (_, a), (_, b) in zip(new.named_parameters(), ref.named_parameters()):
+            a.requires_grad_(b.requires_grad)
+        return new
+
     def forward(self, features, sample_locs_dict=None, cond_frame_index=None, epipolar_F=None, **kwargs):
         """features [B, T, C, H, W] -> [(B H W), T, C]."""
         B, T, c, H, W = features.shape
@@ -617,7 +702,7 @@ class Epipolar(nn.Module):
         return y.view(B, T, H * W, c).permute(0, 2, 1, 3).reshape(B * H * W, T, c)
 
 
-class BasicTransformerBlock(_Prepared):
+class BasicTransformerBlock(_RefBindable, _Prepared):
     """attention.py:214-253 plus the camera-conditioned temporal variant (modified_forwards.py:505-536):
         spatial : x = attn1(LN1 x) + x ; x = attn2(LN2 x, context) + x ; x = FF(LN3 x) + x
         temporal: n = LN1 x ; z = pluker_projection(n + p) + Epipolar(n + p) ; x = z + attn1(n) + x ; ...
@@ -653,6 +738,20 @@ class BasicTransformerBlock(_Prepared):
                 lin = getattr(self, name)
                 p[name] = (_bf16(lin.weight), _f32(lin.bias))
         return p
+
+    def add_module(self, name, module):
+        """The reference injects camera sub-modules into the temporal blocks by name (`epipolar`, `pluker_projection`,
+        `cc_projection`; camcontexti2v.py:151-166, cameractrl.py, motionctrl.py).  A reference `Epipolar` instance is adopted as
+        this package's class (same parameters); Linear layers are parameter holders as they are.  The block's conditioning
+        variant follows from what was injected."""
+        if name == "epipolar" and module is not None and not isinstance(module, Epipolar):
+            module = Epipolar.adopt(module)
+        super().add_module(name, module)
+        if name in ("epipolar", "pluker_projection"):
+            self.variant = "camcontext"
+        elif name == "cc_projection" and module is not None:
+            self.variant = "motionctrl" if module.in_features != module.out_features else "cameractrl"
+        self._pk = None
 
     def origin_h(self) -> int:
         """Pixel size of the full frame the epipolar grid refers to (Epipolar.origin_h, epipolar.py:112-113)."""
@@ -755,8 +854,7 @@ def _tile_map(Fm: torch.Tensor, T: int, H: int, W: int, d: int):
     key = (Fm.data_ptr(), tuple(Fm.shape), T, H, W, d)
     ent = _TILEMAP_CACHE.get(key)
     if ent is None:
-        if len(_TILEMAP_CACHE) > 64:
-            _TILEMAP_CACHE.clear()
+        _evict(_TILEMAP_CACHE, 64)
         ent = _TILEMAP_CACHE[key] = [Fm._version, ops.epipolar_tile_map(Fm, T, H, W, d), Fm]
     elif ent[0] != Fm._version:
         ent[0] = Fm._version
@@ -771,8 +869,7 @@ def _bitmask(Fm: torch.Tensor, T: int, H: int, W: int, d: int):
     key = (Fm.data_ptr(), tuple(Fm.shape), T, H, W, d)
     ent = _BITMASK_CACHE.get(key)
     if ent is None:
-        if len(_BITMASK_CACHE) > 64:
-            _BITMASK_CACHE.clear()
+        _evict(_BITMASK_CACHE, 64)
         ent = _BITMASK_CACHE[key] = [Fm._version, ops.epipolar_bitmask(Fm, T, H, W, d), Fm]
     elif ent[0] != Fm._version:
         ent[0] = Fm._version
@@ -787,8 +884,7 @@ def _pluker_cl(p: torch.Tensor) -> torch.Tensor:
     B, C, T, h, w = p.shape
     ent = _PLUKER_CACHE.get(key)
     if ent is None:
-        if len(_PLUKER_CACHE) > 64:
-            _PLUKER_CACHE.clear()
+        _evict(_PLUKER_CACHE, 64)
         ent = _PLUKER_CACHE[key] = [p._version, ops.to_channels_last(_f32(p), B, C, T * h * w), p]
     elif ent[0] != p._version:
         ent[0] = p._version
@@ -869,7 +965,7 @@ class SpatialTransformer(_Prepared):
         return ops.from_channels_last(y, n, c, hh * ww).view(n, c, hh, ww)
 
 
-class TemporalTransformer(_Prepared):
+class TemporalTransformer(_RefBindable, _Prepared):
     """attention.py:323-428 (only_self_att=True) with the camera-conditioned forward of modified_forwards.py:401-450."""
 
     def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0.0, context_dim=None, use_checkpoint=True, use_linear=False,
@@ -915,7 +1011,7 @@ class TemporalTransformer(_Prepared):
         return ops.from_channels_last(y, b, c, t * hh * ww).view(b, c, t, hh, ww)
 
 
-class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+class TimestepEmbedSequential(_RefBindable, nn.Sequential, TimestepBlock):
     """openaimodel3d.py:30-48 with the camera_condition argument of modified_forwards.py:384-398."""
 
     def forward_cl(self, h, emb, ctx, dm: Dims, cam: Optional[CameraLevel], h_bf16=None):
@@ -960,7 +1056,7 @@ class _ConvIn(_Prepared):
         self.conv = nn.Conv2d(cin, cout, 3, padding=1)
 
 
-class UNetModel(_Prepared):
+class UNetModel(_RefBindable, _Prepared):
     """lvdm 3D-UNet (openaimodel3d.py:281-624) with the camera-conditioned forward (modified_forwards.py:29-131).
 
     Constructor keywords follow the reference; only the configuration space used by

@@ -266,10 +266,11 @@ def epipolar_mask(F: torch.Tensor, H: int, W: int, d: int) -> torch.Tensor:
 
 def epipolar_bitmask(F: torch.Tensor, T: int, H: int, W: int, d: int, out=None):
     """The epipolar mask packed to bits for attention(..., epi_F=F, epi_bitmask=...): int32 [B, q_tiles, k_chunks, 128]
-    (bit i of word [b, qt, c, r] = mask[b, 128 qt + r, 32 c + i]); None when the grid has no fast path."""
+    (bit i of word [b, qt, c, r] = mask[b, 128 qt + r, 32 c + i]); any grid whose token count is a multiple of 128 (the five
+    power-of-two grids of the shipped resolutions have a specialised builder); None otherwise."""
     _chk(F, F32, "epipolar_bitmask.F")
     L = T * H * W
-    if H != W or (W, d) not in ((32, 8), (16, 16), (8, 32), (16, 8), (8, 16)) or L % 128:
+    if L % 128:
         return None
     B = F.shape[0]
     if out is None:

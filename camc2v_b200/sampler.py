@@ -55,7 +55,9 @@ class DiffusionWrapper(nn.Module):
 
     def forward(self, x, t, c_concat: list = None, c_crossattn: list = None, **kwargs):
         xc = torch.cat([x] + c_concat, dim=1)
-        cc = torch.cat(c_crossattn, 1)
+        # A single context tensor is passed through as it is: its address is then stable over the sampling loop, which is what
+        # lets make_context_pack / CrossAttention._context_kv keep the bf16 tokens and the projected K/V per sample.
+        cc = c_crossattn[0] if len(c_crossattn) == 1 else torch.cat(c_crossattn, 1)
         return self.diffusion_model(xc, t, context=cc, **kwargs)
 
 
@@ -86,15 +88,39 @@ class DenoiserModel(nn.Module):
         return out[0] if isinstance(out, tuple) else out
 
 
+def _leaf_key(o):
+    """Identity of a conditioning structure for the CUDA-graph cache: every tensor leaf by (id, address, shape, dtype), plain
+    values by value.  The graph entry also keeps the structure itself alive, so neither ids nor addresses can be recycled.
+    In-place refills of a leaf (same address) deliberately do NOT change the key: that is the supported way to reuse a captured
+    graph for the next video (refresh_camera_caches / refresh_context_caches re-derive the cached state in place)."""
+    if isinstance(o, torch.Tensor):
+        return ("T", id(o), o.data_ptr(), tuple(o.shape), str(o.dtype))
+    if isinstance(o, dict):
+        return ("D",) + tuple((k, _leaf_key(v)) for k, v in o.items())
+    if isinstance(o, (list, tuple)):
+        return ("L",) + tuple(_leaf_key(v) for v in o)
+    if o is None or isinstance(o, (bool, int, float, str)):
+        return ("V", o)
+    return ("O", id(o))
+
+
 class DDIMSampler(object):
     def __init__(self, model, schedule="linear", **kwargs):
+        if getattr(model, "parameterization", "eps") != "eps":
+            raise NotImplementedError(f"parameterization {model.parameterization!r}: only eps-prediction models are sampled (ddim.py:285-288)")
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
         self._graph = None
         self.concurrent_passes = kwargs.get("concurrent_passes", True)
         self.cfg_pair = kwargs.get("cfg_pair", None)       # parallel.CfgPair: split the CFG halves over two ranks
-        self._derived = {}                                  # conditioning dicts derived from the caller's (stable identity for the graph key)
+
+    def reset_graph(self):
+        """Drop the captured CUDA graph (and the references it holds to conditioning tensors and cache-derived buffers)."""
+        if self._graph is not None:
+            from . import modules
+            modules.unpin_caches(self._graph.get("pin"))
+        self._graph = None
 
     # -------------------------------------------------------------------------------------------- schedule
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
@@ -115,23 +141,26 @@ class DDIMSampler(object):
 
     # -------------------------------------------------------------------------------------------- sampling
     @torch.no_grad()
-    def sample(self, S, batch_size, shape, conditioning=None, eta=0., temperature=1., verbose=False, x_T=None,
-               unconditional_guidance_scale=1., unconditional_conditioning=None, fs=None, timestep_spacing='uniform',
-               guidance_rescale=0.0, use_cuda_graph=False, **kwargs):
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None, quantize_x0=False,
+               eta=0., mask=None, x0=None, temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None, verbose=False,
+               schedule_verbose=False, x_T=None, log_every_t=100, unconditional_guidance_scale=1., unconditional_conditioning=None,
+               precision=None, fs=None, timestep_spacing='uniform', guidance_rescale=0.0, use_cuda_graph=False, **kwargs):
+        """ddim.py:59-132, same keyword list.  Options outside the CamContextI2V sampling protocol raise NotImplementedError
+        (they are never silently ignored): quantize_x0, mask / x0 blending, noise_dropout, score_corrector, precision=16."""
+        if quantize_x0 or mask is not None or x0 is not None or noise_dropout > 0. or score_corrector is not None or precision is not None:
+            raise NotImplementedError("DDIMSampler.sample: quantize_x0 / mask / x0 / noise_dropout / score_corrector / precision are "
+                                      "outside the per-step scope (ddim.py:176-183, 289-296, 340-343)")
         self.make_schedule(ddim_num_steps=S, ddim_discretize=timestep_spacing, ddim_eta=eta, verbose=False)
-        if len(shape) == 3:
-            size = (batch_size,) + tuple(shape)
-        else:
-            size = (batch_size,) + tuple(shape)
-        return self.ddim_sampling(conditioning, size, x_T=x_T, temperature=temperature,
-                                  unconditional_guidance_scale=unconditional_guidance_scale,
+        size = (batch_size,) + tuple(shape)
+        return self.ddim_sampling(conditioning, size, x_T=x_T, temperature=temperature, callback=callback, img_callback=img_callback,
+                                  log_every_t=log_every_t, unconditional_guidance_scale=unconditional_guidance_scale,
                                   unconditional_conditioning=unconditional_conditioning, fs=fs,
                                   guidance_rescale=guidance_rescale, use_cuda_graph=use_cuda_graph, **kwargs)
 
     @torch.no_grad()
     def ddim_sampling(self, cond, shape, x_T=None, temperature=1., unconditional_guidance_scale=1.,
                       unconditional_conditioning=None, fs=None, guidance_rescale=0.0, log_every_t=100, use_cuda_graph=False,
-                      img_callback=None, **kwargs):
+                      img_callback=None, callback=None, **kwargs):
         """ddim.py:134-238 (the mask / paste / noise-shaping editing branches are outside the per-step scope)."""
         device = self.model.betas.device
         b = shape[0]
@@ -146,6 +175,8 @@ class DDIMSampler(object):
                                               unconditional_guidance_scale=unconditional_guidance_scale,
                                               unconditional_conditioning=unconditional_conditioning, fs=fs,
                                               guidance_rescale=guidance_rescale, use_cuda_graph=use_cuda_graph, **kwargs)
+            if callback:
+                callback(i)
             if img_callback:
                 img_callback(pred_x0, i)
             if index % log_every_t == 0 or index == total_steps - 1:
@@ -160,8 +191,9 @@ class DDIMSampler(object):
         if not use_cuda_graph:
             return [self.model.apply_model(x, t, c, **kwargs) for c in conds]
         g = self._graph
-        key = (tuple(id(c) for c in conds), tuple(x.shape))
+        key = (_leaf_key(conds), _leaf_key(kwargs), tuple(x.shape), str(x.dtype))
         if g is None or g["key"] != key:
+            self.reset_graph()
             sx, st = x.clone(), t.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -189,7 +221,11 @@ class DDIMSampler(object):
                         outs.append(self.model.apply_model(sx, st, c, **kwargs))
                 for br in branches:
                     main.wait_stream(br)
-            g = self._graph = dict(key=key, graph=graph, x=sx, t=st, outs=outs, ec=outs[0], eu=outs[-1])
+            from . import modules
+            # `refs` keeps every conditioning tensor of the key alive; `pin` marks the cache-derived buffers the captured kernels
+            # point at (tile maps, packed masks, channels-last Pluecker copies, context packs, projected K/V) as non-evictable.
+            g = self._graph = dict(key=key, graph=graph, x=sx, t=st, outs=outs, ec=outs[0], eu=outs[-1], refs=(list(conds), dict(kwargs)),
+                                   pin=modules.pin_caches(self.model))
         g["x"].copy_(x)
         g["t"].copy_(t)
         g["graph"].replay()
@@ -209,6 +245,14 @@ class DDIMSampler(object):
         the same point of the RNG stream as the reference (ddim.py:340)."""
         if use_original_steps or quantize_denoised or score_corrector is not None or noise_dropout > 0. or repeat_noise:
             raise NotImplementedError("option outside the CamContextI2V sampling protocol")
+        if mask is not None or x0 is not None:
+            raise NotImplementedError("mask / x0 blending (ddim.py:176-183) is outside the per-step scope")
+        for opt in ("paste_cond_frame", "paste_overlap_frames", "noise_shaping", "timesteps", "precision", "clean_cond"):
+            if kwargs.get(opt):
+                raise NotImplementedError(f"{opt} (ddim.py:150-238 editing branches) is outside the per-step scope")
+            kwargs.pop(opt, None)
+        if getattr(self.model, "parameterization", "eps") != "eps":
+            raise NotImplementedError("only eps-prediction models are sampled (ddim.py:285-288)")
         a_t = float(self.ddim_alphas[index])
         a_prev = float(self.ddim_alphas_prev[index])
         sigma_t = float(self.ddim_sigmas[index])
@@ -232,11 +276,8 @@ class DDIMSampler(object):
                 # camera guidance (ddim.py:268-280): a third pass, conditional but without the camera condition
                 if self.cfg_pair is not None:
                     raise NotImplementedError("camera_cfg != 1 together with CFG-split")
-                key = ("nocam", id(c))
-                c_nc = self._derived.get(key)
-                if c_nc is None:
-                    self._derived.clear()
-                    c_nc = self._derived[key] = {k: v for k, v in c.items() if k != "camera_condition"}
+                # a shallow copy per step; the CUDA-graph key compares tensor leaves, not dict identities
+                c_nc = {k: v for k, v in c.items() if k != "camera_condition"}
                 e_c, e_u, e_nc = self._unet_passes(x, t, [c, uc, c_nc], kwargs, use_cuda_graph)
                 # scheduler weight from the HOST copy of the timestep (ddim_timesteps[index] == t): no device sync
                 w = 1.0 if camera_cfg_scheduler == "constant" else math.cos((1.0 - float(self.ddim_timesteps[index]) / 999.0) * math.pi / 2.0)

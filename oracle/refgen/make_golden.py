@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU (build container only).
 
-    python oracle/refgen/make_golden.py [--only masks|unet_small|ddim|unet_full] [--check-oracle]
+    python oracle/refgen/make_golden.py [--only masks|unet_small|ddim|unet_full|loop_full] [--check-oracle]
 
 The reference has no tests or golden vectors of its own; these files are outputs of the
 reference's own code (imported from /root/reference by ref_harness.py) on seeded synthetic inputs that
@@ -204,6 +204,46 @@ def gen_unet_full(check):
         t0 = time.time()
         y = orc.forward(xc, t, inp["ctx_cond"], inp["fs"], cam)
         print(f"    oracle cond pass {time.time() - t0:.1f}s; vs reference rel-L2 {rel_err(y, y_c)[0]:.3e} max-norm {rel_err(y, y_c)[1]:.3e}")
+
+
+def gen_loop_full(check, steps_saved=(1, 2, 5, 10, 15, 20, 25)):
+    """The north star's acceptance case at FULL size: the reference's own DDIMSampler.sample (25 steps, uniform_trailing, eta 1,
+    CFG 3.5, guidance_rescale 0.7, camera condition on both CFG branches) on the 1500.9 M-parameter UNet, 256x256x16f, batch 1,
+    845-token context (1 reference + 2 context frames), epipolar masks at all four levels.  x_T = the `full` synthetic latent,
+    eta-noise from torch's CPU generator seeded 20230211 right before the call (one randn per step, ddim.py:340).
+    About 1 min of CPU per step on 8 cores (25 min in total).  The first saved step doubles as the golden of ONE full-size
+    p_sample_ddim call (index 24, t = 999)."""
+    cfg = UNetConfig()
+    t0 = time.time()
+    model = build_ref(None, None)
+    print(f"  full model built+filled in {time.time() - t0:.0f}s")
+    inp = synth_inputs(cfg, 32, 2, "full")
+    cam, F = camera_condition(model, 256, "pan_yaw", inp["pluker"])
+    DDIM = rh.patch_ddim_for_cpu()
+    sampler = DDIM(model)
+    cond = {"c_crossattn": [inp["ctx_cond"]], "c_concat": [inp["c_concat"]], "camera_condition": cam}
+    uc = {"c_crossattn": [inp["ctx_uncond"]], "c_concat": [inp["c_concat"]]}
+    out = {"F": F.numpy(), "seed": np.int64(20230211), "steps_saved": np.asarray(steps_saved, dtype=np.int64)}
+    tt = [time.time()]
+
+    def cb(i):
+        tt.append(time.time())
+        print(f"    step {i + 1}/25: {tt[-1] - tt[-2]:.1f}s", flush=True)
+
+    torch.manual_seed(20230211)
+    samples, inter = sampler.sample(25, 1, tuple(inp["x"].shape[1:]), conditioning=cond, eta=1.0, verbose=False, x_T=inp["x"],
+                                    unconditional_guidance_scale=3.5, unconditional_conditioning=uc, fs=inp["fs"],
+                                    timestep_spacing="uniform_trailing", guidance_rescale=0.7, enable_camera_condition=True,
+                                    log_every_t=1, callback=cb)
+    # intermediates[k] = state after k steps (entry 0 is x_T), ddim.py:156, 229-231
+    assert len(inter["x_inter"]) == 26 and torch.equal(inter["x_inter"][-1], samples)
+    for k in steps_saved:
+        out[f"x_step{k}"] = inter["x_inter"][k].numpy()
+        out[f"pred_x0_step{k}"] = inter["pred_x0"][k].numpy()
+    out["sec_per_step"] = np.float64((tt[-1] - tt[0]) / 25)
+    out["threads"] = np.int64(torch.get_num_threads())
+    print(f"  25-step FULL-SIZE reference loop: {tt[-1] - tt[0]:.0f}s, final std {samples.std():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "loop_full.npz"), **out)
 
 
 def gen_variants(check):
@@ -480,3 +520,6 @@ if __name__ == "__main__":
     if a.only in ("unet_full",):
         print("[unet_full]")
         gen_unet_full(a.check_oracle)
+    if a.only in ("loop_full",):
+        print("[loop_full]")
+        gen_loop_full(a.check_oracle)

@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  It is used (a) to pin `oracle/` against the reference's own code and
 (b) to generate the golden vectors committed under `tests/golden/` (see `make_golden.py`).
-It cannot run on the GPU box (`/root/reference` does not exist there) and nothing in the
-product path (`camc2v_b200/`), `bench.py` or the `-m gpu` tests imports it.
+Nothing in the product path (`camc2v_b200/`) imports it.  On the GPU box `/root/reference` does not exist: there the harness
+imports the byte-identical copies that `install_ref.py` placed under `oracle/_ref/` (git-ignored, shipped with the snapshot), and
+only `bench.py --impl reference`, `bench.py`'s `cpu_baseline` leg and the drop-in tests (tests/test_dropin_gpu.py) use it.
 
 What it does:
   * installs a ~20-line stub `pytorch_lightning` (absent in this image) so that
@@ -27,7 +28,20 @@ import torch
 import torch.nn as nn
 import yaml
 
-REF_ROOT = os.environ.get("CAMC2V_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_INSTALLED = os.path.abspath(os.path.join(_HERE, "..", "_ref"))          # oracle/_ref (install_ref.py)
+
+
+def _find_reference() -> str:
+    env = os.environ.get("CAMC2V_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/CamContextI2V"):
+        return "/root/reference"
+    return _INSTALLED
+
+
+REF_ROOT = _find_reference()
 REF_PKG = os.path.join(REF_ROOT, "CamContextI2V")
 REF_CFG = os.path.join(REF_ROOT, "configs")
 
@@ -109,10 +123,13 @@ def load_model_config(name="models/camcontexti2v_256.yaml"):
 IDENTITY = {"target": "torch.nn.Identity"}
 
 
-def build_reference_model(unet_overrides: dict | None = None, seed: int = 0):
+def build_reference_model(unet_overrides: dict | None = None, seed: int = 0, unet_target: str | None = None):
     """Construct the reference CamContextI2V (UNet + patches + Epipolar + pluker_projection) on CPU.
 
     unet_overrides: optional overrides of unet_config.params (e.g. a small model_channels for fast tests).
+    unet_target: optional replacement of `unet_config.target` (the YAML swap of INTEGRATION.md section 2, e.g.
+        "camc2v_b200.modules.UNetModel"); everything else - the reference's constructor with its by-name forward re-binding and
+        sub-module injection, LatentDiffusion.apply_model, DiffusionWrapper - stays the reference's own code.
     """
     setup_reference_imports()
     from model.camcontexti2v import CamContextI2V  # noqa
@@ -130,6 +147,8 @@ def build_reference_model(unet_overrides: dict | None = None, seed: int = 0):
     if unet_overrides:
         for k, v in unet_overrides.items():
             p.unet_config.params[k] = v
+    if unet_target:
+        p.unet_config.target = unet_target
     torch.manual_seed(seed)
     try:
         model = CamContextI2V(**p)

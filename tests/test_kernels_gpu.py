@@ -281,6 +281,19 @@ def test_attention_epipolar(T, H, W, d, heads, kind):
         out_b2 = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm.to(DEV).contiguous(), epi_grid=(T, H, W),
                                epi_d=d, epi_bitmask=bm)
         assert torch.equal(out, out_b2)
+    elif L % 128 == 0:
+        # grids without a specialised builder (the 4x4 level, d = 64: a 32-key chunk spans two frames) use the generic packed-mask
+        # builder; the attention kernel then never evaluates a predicate
+        nt = L // 128
+        bm = ops.epipolar_bitmask(Fm.to(DEV).contiguous(), T, H, W, d)
+        assert bm is not None and bm.shape == (1, nt, L // 32, 128)
+        w = bm[0].cpu().numpy().astype(np.uint32)
+        unpacked = ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)
+        unpacked = np.transpose(unpacked, (0, 2, 1, 3)).reshape(nt * 128, L)
+        assert np.array_equal(unpacked, mask[0].cpu().numpy()), "generic packed epipolar mask differs from the reference mask"
+        out_b = ops.attention(q, k, v, 1, L, L, heads, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm.to(DEV).contiguous(), epi_grid=(T, H, W),
+                              epi_d=d, epi_bitmask=bm)
+        assert torch.equal(out, out_b)
 
 
 @pytest.mark.parametrize("B,T,HW,heads", [(1, 16, 1024, 5), (2, 16, 64, 20), (1, 16, 256, 8), (1, 8, 16, 4)])

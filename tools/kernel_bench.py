@@ -106,15 +106,19 @@ def bench_attn():
         print(f"  {bq:3d} {lq:5d} {lk:5d} {h:3d} {div:3d}  {us:8.1f} us  {4.0 * bq * lq * lk * C / us / 1e6:7.1f} TFLOP/s")
     print("== epipolar attention: T H W d heads trajectory")
     for kind in ("pan_yaw", "dolly", "stationary"):
-        for T, H, d, h in [(16, 32, 8, 5), (16, 16, 16, 10), (16, 8, 32, 20)]:
+        for T, H, d, h in [(16, 32, 8, 5), (16, 16, 16, 10), (16, 8, 32, 20), (16, 4, 64, 20)]:
             L, C = T * H * H, h * 64
             qkv, reg = rb(L, 3 * C), rb(4, 2 * C)
             K, w2c = synth.synth_camera(kind, T=T)
             torch.manual_seed(123)
             Fm = camera.fundamental_matrices(K, camera.relative_c2w(w2c, torch.zeros(1, dtype=torch.long))).to(DEV).contiguous()
+            tmap = ops.epipolar_tile_map(Fm, T, H, H, d)       # once per sample, as in the model path
+            bmask = ops.epipolar_bitmask(Fm, T, H, H, d)
             us = timeit(lambda: ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], 1, L, L, h, k2=reg[:, :C], v2=reg[:, C:], epi_F=Fm,
-                                              epi_grid=(T, H, H), epi_d=d))
-            print(f"  {kind:11s} {T:3d} {H:3d} {d:3d} {h:3d}  {us:8.1f} us  {4.0 * L * (L + 4) * C / us / 1e6:7.1f} TFLOP/s (dense-equivalent)")
+                                              epi_grid=(T, H, H), epi_d=d, epi_tile_map=tmap, epi_bitmask=bmask))
+            vis = 1.0 if tmap is None else float(sum(bin(int(w) & 0xffffffff).count("1") for w in tmap[..., :-1].flatten().tolist())) / ((L // 128) * (L // 64))
+            print(f"  {kind:11s} {T:3d} {H:3d} {d:3d} {h:3d}  {us:8.1f} us  {4.0 * L * (L + 4) * C / us / 1e6:7.1f} TFLOP/s (dense-equivalent; "
+                  f"{vis * 100:.1f}% of tiles visited -> {4.0 * L * (L + 4) * C * vis / us / 1e6:7.1f} executed)")
     print("== temporal attention: B T HW heads")
     for B, T, HW, h in [(1, 16, 1024, 5), (1, 16, 1024, 8), (1, 16, 256, 10), (1, 16, 64, 20)]:
         qkv = rb(B * T * HW, 3 * h * 64)
