@@ -292,6 +292,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=1, help="videos per GPU")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="videos of the whole job (BASELINE.json configs[3]/[4]: 32): split evenly over the GPUs (over the rank pairs with "
+                         "--cfg-split); overrides --batch")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--serial-passes", action="store_true", help="do not overlap the cond / uncond UNet passes inside the CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -331,6 +334,10 @@ def main():
         from camc2v_b200.parallel import make_cfg_pairs
         pair = make_cfg_pairs(rank, world)
     units = world // 2 if pair is not None else world          # independent video streams of the job
+    if args.global_batch:
+        if args.global_batch % units:
+            raise SystemExit(f"--global-batch {args.global_batch} is not a multiple of the {units} video streams of this job")
+        B = args.global_batch // units
     model, sampler, host, cam_host, _ = build_workload(cfg, B, device, seed_offset=(rank // 2 if pair is not None else rank),
                                                        variant=args.variant)
     sampler.cfg_pair = pair

@@ -54,7 +54,7 @@ class AttnDesc(C.Structure):
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 
-# name -> (restype, argtypes); must list every symbol of include/camc2v_b200.h (tests/test_abi.py checks).
+# name -> (restype, argtypes); must list every symbol of include/camc2v_b200.h (tests/test_host_cpu.py checks both directions).
 PROTOTYPES = {
     "c2v_abi_version": (_i, []),
     "c2v_operand_dtype": (_i, []),
@@ -85,6 +85,8 @@ PROTOTYPES = {
     "c2v_from_channels_last": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "c2v_concat_channels": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "c2v_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "c2v_concat_channels_scaled": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp]),
+    "c2v_cast_bf16_scaled": (_i, [_vp, _vp, _i64, _f, _vp]),
     "c2v_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "c2v_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "c2v_im2col_s2_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -388,12 +388,23 @@ int c2v_from_channels_last(const float* in, float* out, int B, int C, int S, voi
 
 int c2v_concat_channels(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, void* stream) {
     if (!a || !b || (!out_f32 && !out_bf16)) return ERR_BAD_ARG;
-    return concat_channels_launch(a, b, out_f32, out_bf16, rows, Ca, Cb, (cudaStream_t)stream);
+    return concat_channels_launch(a, b, out_f32, out_bf16, rows, Ca, Cb, 1.0f, (cudaStream_t)stream);
+}
+
+int c2v_concat_channels_scaled(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, float scale16,
+                               void* stream) {
+    if (!a || !b || (!out_f32 && !out_bf16) || !(scale16 > 0.0f)) return ERR_BAD_ARG;
+    return concat_channels_launch(a, b, out_f32, out_bf16, rows, Ca, Cb, scale16, (cudaStream_t)stream);
 }
 
 int c2v_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
     if (!in || !out || n <= 0) return ERR_BAD_ARG;
-    return cast_bf16_launch(in, out, n, (cudaStream_t)stream);
+    return cast_bf16_launch(in, out, n, 1.0f, (cudaStream_t)stream);
+}
+
+int c2v_cast_bf16_scaled(const float* in, void* out, int64_t n, float scale, void* stream) {
+    if (!in || !out || n <= 0 || !(scale > 0.0f)) return ERR_BAD_ARG;
+    return cast_bf16_launch(in, out, n, scale, (cudaStream_t)stream);
 }
 
 int c2v_upsample2x(const float* in, void* out, int N, int H, int W, int C, void* stream) {

@@ -45,6 +45,15 @@ constexpr int FA_D = 64;
 #ifndef C2V_FA_POLY
 #define C2V_FA_POLY 0
 #endif
+// debug builds only (-DC2V_FA_TIMING=1): warp 2 of a few CTAs prints its per-phase cycle totals (clock64) at the end
+#ifndef C2V_FA_TIMING
+#define C2V_FA_TIMING 0
+#endif
+#if C2V_FA_TIMING
+#define FA_T(i) do { const long long _t = clock64(); tacc[i] += _t - tlast; tlast = _t; } while (0)
+#else
+#define FA_T(i) do { } while (0)
+#endif
 constexpr int FA_KV_STAGES = C2V_FA_KV_STAGES;
 constexpr int FA_THREADS = 192;
 constexpr float FA_TAU = 8.0f;                       // lazy-rescale threshold (log2 units): P <= 2^8
@@ -60,8 +69,9 @@ constexpr int FA_OFF_LIST = FA_OFF_BAR + 256;
 constexpr int FA_MAX_TILES = 1024;
 constexpr int FA_SMEM = FA_OFF_LIST + FA_MAX_TILES * 2;
 
-constexpr uint32_t FA_TM_S = 0;                      // S / P buffers: 2 x 64 columns (P = first 32 columns of its S buffer)
+constexpr uint32_t FA_TM_S = 0;                      // S buffers: 2 x 64 fp32 columns
 constexpr uint32_t FA_TM_O = 2 * FA_BN;              // O accumulator: 64 columns
+constexpr uint32_t FA_TM_P = FA_TM_O + FA_D;         // P buffers: 2 x 32 columns (64 keys as 16-bit pairs)
 constexpr uint32_t FA_TMEM_COLS = 256;
 
 constexpr uint32_t FA_NEG_INF = 0xff800000u;
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t v_addr = smem_u32(smem + FA_OFF_V + s * FA_V_BYTES);
-                    const uint32_t p_tmem = tmem_base + FA_TM_S + (uint32_t)(j & 1) * FA_BN;
+                    const uint32_t p_tmem = tmem_base + FA_TM_P + (uint32_t)(j & 1) * (FA_BN / 2);
 #pragma unroll
                     for (int ks = 0; ks < FA_BN / 16; ++ks) {
                         const uint64_t vd = umma_desc_sw128(v_addr + ks * 16 * 128);
@@ -276,6 +286,7 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
         const int qi = q0 + r;                                     // query index inside the batch
         const uint32_t t_s0 = tmem_base + FA_TM_S + ((uint32_t)(lg * 32) << 16);
         const uint32_t t_o = tmem_base + FA_TM_O + ((uint32_t)(lg * 32) << 16);
+        const uint32_t t_p0 = tmem_base + FA_TM_P + ((uint32_t)(lg * 32) << 16);
         const bool epi = p.epi_F != nullptr;
         const bool use_words = MODE == 0 && epi && p.bitmask != nullptr;
         const unsigned char* mrow = (MODE == 1 && p.mask) ? p.mask + (size_t)b * p.mask_bstride + (size_t)min(qi, p.lq - 1) * p.lk : nullptr;
@@ -296,10 +307,10 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
         float l0x[MODE == 2 ? (1 << LOGW) : 1];
 
         float m_ref = -INFINITY;   // reference maximum of the exponentials (log2 domain), raised lazily
-        float l_run = 0.f;
+        float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // running row sum, four independent partial sums
 
         const uint32_t* wbase = use_words ? p.bitmask + ((size_t)b * gridDim.x + q_tile) * (size_t)(p.lk >> 5) * FA_BM + r : nullptr;
-        uint32_t bw_n[2] = {0u, 0u};                       // packed mask words of the NEXT tile (fetched one tile ahead)
+        uint32_t bw_n[2] = {0u, 0u};                       // packed mask words fetched one tile ahead of their use
         auto fetch_words = [&](int jt_, uint32_t (&w)[2]) {
             if (jt_ < n_main) {
                 const uint32_t* q = wbase + (size_t)jt_ * 2 * FA_BM;
@@ -307,15 +318,26 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
                 w[1] = __ldg(q + FA_BM);
             }
         };
-        if (use_words && n_act > 0) fetch_words(tile_list[0], bw_n);
-
-        for (int j = 0; j < n_act; ++j) {
-            const int jt = tile_list[j];
+        // Mask words of this row for the two 32-key chunks of visited tile `it` (bit i = key (chunk base + i) is attended) and
+        // the warp-uniform flags derived from them: act = some row of the warp attends a key of the chunk (else the chunk is never
+        // read, its probabilities are stored as zeros), full = no row masks anything (the select is skipped).
+        struct TileInfo {
+            uint32_t w0, w1;
+            bool act0, act1, full0, full1;
+        };
+        auto tile_info = [&](int it) -> TileInfo {
+            const int jt = tile_list[it];
             const bool main_seg = jt < n_main;
             const int klim = main_seg ? p.lk : p.lk2;
             const int tile_key0 = main_seg ? jt * FA_BN : 0;
-            // ---- mask words of this row for the tile's two 32-key chunks: bit i = key (chunk base + i) is attended ----
+            TileInfo ti;
+            if (!(main_seg && (epi || mrow)) && tile_key0 + FA_BN <= klim) {      // dense tile, fully inside the sequence: no votes
+                ti.w0 = ti.w1 = 0xffffffffu;
+                ti.act0 = ti.act1 = ti.full0 = ti.full1 = true;
+                return ti;
+            }
             uint32_t bw[2];
+            // ---- mask words of this row for the tile's two 32-key chunks: bit i = key (chunk base + i) is attended ----
             if (use_words && main_seg) {
                 bw[0] = bw_n[0];
                 bw[1] = bw_n[1];
@@ -411,96 +433,125 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
                     bw[c] = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
                 }
             }
-            if (use_words && j + 1 < n_act) fetch_words(tile_list[j + 1], bw_n);
-            // rows past lq (ragged last query tile) run like every other row; their output is never stored
-            const bool act0 = __any_sync(0xffffffffu, bw[0] != 0u);
-            const bool act1 = __any_sync(0xffffffffu, bw[1] != 0u);
-            const bool full0 = __all_sync(0xffffffffu, bw[0] == 0xffffffffu);
-            const bool full1 = __all_sync(0xffffffffu, bw[1] == 0xffffffffu);
+            ti.w0 = bw[0];
+            ti.w1 = bw[1];
+            ti.act0 = __any_sync(0xffffffffu, bw[0] != 0u);
+            ti.act1 = __any_sync(0xffffffffu, bw[1] != 0u);
+            ti.full0 = __all_sync(0xffffffffu, bw[0] == 0xffffffffu);
+            ti.full1 = __all_sync(0xffffffffu, bw[1] == 0xffffffffu);
+            return ti;
+        };
 
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t t_s = t_s0 + (uint32_t)(j & 1) * FA_BN;
-            uint32_t v0[32], v1[32];
-            if (act0) tmem_ld32(t_s, v0);
-            if (act1) tmem_ld32(t_s + 32, v1);
-            tmem_ld_wait();
-            float mx = -INFINITY;
-            if (act0) {
-                if (!full0) {
+        // O *= alpha (rows of this thread): only on the rare tiles where the reference maximum is raised
+        auto rescale_o = [&](float alpha) {
+            tmem_st_wait();                                           // an earlier rescale of the same tile may still be in flight
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v0[i] = (bw[0] >> i) & 1u ? v0[i] : FA_NEG_INF;
-                }
-                mx = fa_max32(v0);
-            }
-            if (act1) {
-                if (!full1) {
+            for (int c = 0; c < 4; ++c) {
+                uint32_t o[16];
+                tmem_ld16(t_o + c * 16, o);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v1[i] = (bw[1] >> i) & 1u ? v1[i] : FA_NEG_INF;
-                }
-                mx = fmaxf(mx, fa_max32(v1));
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st16(t_o + c * 16, o);
             }
-            // ---- lazy rescale: raise the reference maximum only when this tile exceeds it by more than 2^TAU ----
-            const float mt = mx * p.scale_log2;                       // scale > 0; -inf stays -inf
-            if (__any_sync(0xffffffffu, mt > m_ref + FA_TAU)) {       // first valid tile of a row: m_ref = -inf -> true
+        };
+        // One 32-key chunk: mask -> max -> (rarely) raise the reference maximum -> exp2 -> 16-bit pairs -> TMEM columns t_pc..+16.
+        // `fix_p0`: TMEM address of the chunk-0 probabilities of the same tile, already stored under the old reference (0 if none).
+        auto chunk = [&](uint32_t (&v)[32], uint32_t word, bool act, bool full, uint32_t t_pc, int j, uint32_t fix_p0) {
+            uint32_t w[16];
+            if (!act) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = 0u;
+                tmem_st16(t_pc, w);
+                return;
+            }
+            if (!full) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = (word >> i) & 1u ? v[i] : FA_NEG_INF;
+            }
+            const float mt = fa_max32(v) * p.scale_log2;               // scale > 0; -inf stays -inf
+            if (__any_sync(0xffffffffu, mt > m_ref + FA_TAU)) {       // first attended key of a row: m_ref = -inf -> true
                 const float m_new = fmaxf(m_ref, mt);
                 const float alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_new);
-                l_run *= alpha;
+                l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
                 m_ref = m_new;
                 if (j > 0) {                                          // O holds PV(0..j-1): wait for PV(j-1), rescale in place
                     mbar_wait(pv_done, (j - 1) & 1);
                     tc_fence_after();
+                    rescale_o(alpha);
+                }
+                if (fix_p0) {                                         // chunk 0 of this tile was stored under the old reference
+                    uint32_t q[16];
+                    tmem_st_wait();
+                    tmem_ld16(fix_p0, q);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t o[32];
-                        tmem_ld32(t_o + c * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(t_o + c * 32, o);
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[i]));
+                        q[i] = pack_bf16(f.x * alpha, f.y * alpha);
                     }
+                    tmem_st16(fix_p0, q);
                 }
             }
             const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-            // ---- probabilities -> 16-bit pairs -> TMEM (over the S columns just consumed) ----
-            float2 l2 = make_float2(0.f, 0.f);
             const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
-            auto probs16 = [&](const uint32_t (&v)[32], uint32_t (&w)[16]) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float2 x = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
-                    float2 e;
-                    constexpr int NP = C2V_FA_POLY;                   // elements per 8 on the FMA pipe
-                    const int pos = (2 * i) & 7;                      // position of the pair's first element in its group of 8
-                    const bool px = pos < NP, py = pos + 1 < NP;
-                    e.x = px ? (v[2 * i] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.x)) : fast_exp2(x.x);
-                    e.y = py ? (v[2 * i + 1] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.y)) : fast_exp2(x.y);
-                    l2 = fadd2(l2, e);
-                    w[i] = pack_bf16(e.x, e.y);
-                }
-            };
-            const uint32_t t_p = t_s;                                 // P(j): columns [0, 32) of S buffer j & 1
-            {
-                uint32_t w[16];
-                if (act0) {
-                    probs16(v0, w);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) w[i] = 0u;
-                }
-                tmem_st16(t_p, w);
+            for (int i = 0; i < 16; ++i) {
+                const float2 x = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+                float2 e;
+                constexpr int NP = C2V_FA_POLY;                   // elements per 8 on the FMA pipe
+                const int pos = (2 * i) & 7;                      // position of the pair's first element in its group of 8
+                const bool px = pos < NP, py = pos + 1 < NP;
+                e.x = px ? (v[2 * i] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.x)) : fast_exp2(x.x);
+                e.y = py ? (v[2 * i + 1] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.y)) : fast_exp2(x.y);
+                if (i & 1) l2b = fadd2(l2b, e);
+                else l2a = fadd2(l2a, e);
+                w[i] = pack_bf16(e.x, e.y);
             }
-            {
-                uint32_t w[16];
-                if (act1) {
-                    probs16(v1, w);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) w[i] = 0u;
-                }
-                tmem_st16(t_p + 16, w);
+            tmem_st16(t_pc, w);
+        };
+
+#if C2V_FA_TIMING
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tlast = clock64();
+        const long long tstart = tlast;
+#endif
+        // Software pipeline over half tiles: while chunk 0 of tile j is processed the load of chunk 1 is in flight, and while chunk 1
+        // is processed the load of chunk 0 of tile j+1 is (v0 is dead by then), so neither the tcgen05.ld latency nor the wait for
+        // S(j+1) sits on the warp's critical path.
+        uint32_t v0[32], v1[32];
+        TileInfo ti = {0u, 0u, false, false, false, false};
+        if (n_act > 0) {
+            if (use_words) fetch_words(tile_list[0], bw_n);
+            ti = tile_info(0);
+            if (use_words && n_act > 1) fetch_words(tile_list[1], bw_n);
+            mbar_wait(&s_full[0], 0);
+            tc_fence_after();
+            if (ti.act0) tmem_ld32(t_s0, v0);
+        }
+        for (int j = 0; j < n_act; ++j) {
+            const uint32_t t_s = t_s0 + (uint32_t)(j & 1) * FA_BN;
+            const uint32_t t_p = t_p0 + (uint32_t)(j & 1) * (FA_BN / 2);
+            tmem_ld_wait();                                           // v0 = S(j) chunk 0
+            if (ti.act1) tmem_ld32(t_s + 32, v1);
+            FA_T(0);
+            chunk(v0, ti.w0, ti.act0, ti.full0, t_p, j, 0u);
+            FA_T(1);
+            TileInfo tn = ti;
+            if (j + 1 < n_act) {
+                tn = tile_info(j + 1);                                // consumes bw_n
+                if (use_words && j + 2 < n_act) fetch_words(tile_list[j + 2], bw_n);
             }
-            l_run += l2.x + l2.y;
+            FA_T(2);
+            tmem_ld_wait();                                           // v1 = S(j) chunk 1
+            if (j + 1 < n_act) {
+                mbar_wait(&s_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                tc_fence_after();
+                if (tn.act0) tmem_ld32(t_s0 + (uint32_t)((j + 1) & 1) * FA_BN, v0);
+            }
+            FA_T(3);
+            chunk(v1, ti.w1, ti.act1, ti.full1, t_p + 16, j, ti.act0 ? t_p : 0u);
+            FA_T(4);
             tmem_st_wait();
             tc_fence_before();
 #if C2V_FA_WARP_ARRIVE
@@ -509,7 +560,16 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
 #else
             mbar_arrive(&p_full[j & 1]);
 #endif
+            ti = tn;
+            FA_T(5);
         }
+        const float l_run = (l2a.x + l2a.y) + (l2b.x + l2b.y);
+#if C2V_FA_TIMING
+        if (lane_id() == 0 && warp == 2 && blockIdx.y == 0 && blockIdx.z == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
+            printf("fa_timing cta %d tiles %d cycles/tile: ld1+wait %lld chunk0 %lld info %lld waitS+ld %lld chunk1 %lld store %lld | total %lld\n",
+                   blockIdx.x, n_act, tacc[0] / n_act, tacc[1] / n_act, tacc[2] / n_act, tacc[3] / n_act, tacc[4] / n_act, tacc[5] / n_act,
+                   (clock64() - tstart) / n_act);
+#endif
         // ---- epilogue: O / l -> 16-bit -> global ----
         if (n_act > 0) {
             mbar_wait(o_final, 0);

@@ -73,8 +73,19 @@ int from_channels_last_launch(const float* in, float* out, int B, int C, int S, 
 // ------------------------------------------------------------------------------------------------
 // channel concat of the skip connection (modified_forwards.py:108), optional bf16 copy for the 1x1 skip conv
 // ------------------------------------------------------------------------------------------------
+// 16-bit copies of UNNORMALISED fp32 data (the residual stream feeding the 1x1 skip convolution): scaled by a power of two chosen by
+// the caller (the consumer's weights carry the inverse, so the product is unchanged) and, in the IEEE-half build, saturated at the
+// largest finite half instead of overflowing to inf.
+__device__ __forceinline__ float sat16(float x) {
+#if C2V_OPERAND_IS_FP16
+    return fminf(fmaxf(x, -65504.0f), 65504.0f);
+#else
+    return x;
+#endif
+}
+
 __global__ void concat_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ of, __nv_bfloat16* __restrict__ ob,
-                              int64_t rows, int Ca, int Cb) {
+                              int64_t rows, int Ca, int Cb, float s16) {
     const int nv = (Ca + Cb) >> 2, nva = Ca >> 2;
     const int64_t total = rows * nv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -83,28 +94,32 @@ __global__ void concat_kernel(const float* __restrict__ a, const float* __restri
         const float4 v = cv < nva ? *reinterpret_cast<const float4*>(a + r * Ca + cv * 4)
                                   : *reinterpret_cast<const float4*>(b + r * Cb + (cv - nva) * 4);
         if (of) *reinterpret_cast<float4*>(of + i * 4) = v;
-        if (ob) *reinterpret_cast<uint2*>(ob + i * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        if (ob)
+            *reinterpret_cast<uint2*>(ob + i * 4) =
+                make_uint2(pack_bf16(sat16(v.x * s16), sat16(v.y * s16)), pack_bf16(sat16(v.z * s16), sat16(v.w * s16)));
     }
 }
 
-int concat_channels_launch(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, cudaStream_t st) {
+int concat_channels_launch(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, float scale16,
+                           cudaStream_t st) {
     if (Ca % 4 || Cb % 4) return ERR_UNSUPPORTED;
-    concat_kernel<<<grid_for(rows * ((Ca + Cb) >> 2), 256), 256, 0, st>>>(a, b, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, Ca, Cb);
+    concat_kernel<<<grid_for(rows * ((Ca + Cb) >> 2), 256), 256, 0, st>>>(a, b, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, Ca, Cb,
+                                                                          scale16);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n4, int64_t n) {
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n4, int64_t n, float s) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = *reinterpret_cast<const float4*>(in + i * 4);
-        *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16(sat16(v.x * s), sat16(v.y * s)), pack_bf16(sat16(v.z * s), sat16(v.w * s)));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (int64_t i = n4 * 4; i < n; ++i) out[i] = __float2bfloat16(in[i]);
+        for (int64_t i = n4 * 4; i < n; ++i) out[i] = __float2bfloat16(sat16(in[i] * s));
 }
 
-int cast_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t st) {
-    cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n / 4, n);
+int cast_bf16_launch(const float* in, void* out, int64_t n, float scale, cudaStream_t st) {
+    cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n / 4, n, scale);
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

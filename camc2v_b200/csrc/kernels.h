@@ -17,8 +17,9 @@ int softmax_rows_launch(const float* x, void* out, int rows, int n, float scale,
 // elementwise.cu
 int to_channels_last_launch(const float* in, void* out, int B, int C, int S, int Cpad, int out_bf16, cudaStream_t st);
 int from_channels_last_launch(const float* in, float* out, int B, int C, int S, cudaStream_t st);
-int concat_channels_launch(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, cudaStream_t st);
-int cast_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t st);
+int concat_channels_launch(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, float scale16,
+                           cudaStream_t st);
+int cast_bf16_launch(const float* in, void* out, int64_t n, float scale, cudaStream_t st);
 int upsample2x_launch(const float* in, void* out, int N, int H, int W, int C, cudaStream_t st);
 int im2col_s2_launch(const float* in, void* out, int N, int H, int W, int C, int pad_lo, cudaStream_t st);
 int copy_rows_launch(const void* src, void* dst, int rows, int C, int B, int64_t dst_bstride, int ldd, cudaStream_t st);

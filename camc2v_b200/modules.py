@@ -297,7 +297,8 @@ class ResBlock(_Prepared, TimestepBlock):
              "g2": _f32(self.out_layers[0].weight), "be2": _f32(self.out_layers[0].bias), "w2": w2, "b2": b2,
              "we": _bf16(self.emb_layers[1].weight), "bemb": _f32(self.emb_layers[1].bias)}
         if not isinstance(self.skip_connection, nn.Identity):
-            p["ws"] = _bf16(self.skip_connection.weight.reshape(self.out_channels, self.channels))
+            # the skip convolution reads a 16-bit copy of the UNNORMALISED residual stream stored at RESIDUAL_PRESCALE (fp16 range)
+            p["ws"] = _bf16(self.skip_connection.weight.reshape(self.out_channels, self.channels) * (1.0 / ops.RESIDUAL_PRESCALE))
             p["bs"] = _f32(self.skip_connection.bias)
         return p
 
@@ -316,7 +317,7 @@ class ResBlock(_Prepared, TimestepBlock):
         h1 = ops.conv3x3(n, p["w1"], dm.BT, dm.H, dm.W, bias=p["b1"], rowbias=e, rows_per_group=dm.T * dm.HW)
         n = ops.groupnorm(h1, p["g2"], p["be2"], dm.BT, dm.HW, 1e-5, True)
         if "ws" in p:
-            skip = ops.linear(h_bf16 if h_bf16 is not None else ops.cast_bf16(h), p["ws"], bias=p["bs"])
+            skip = ops.linear(h_bf16 if h_bf16 is not None else ops.cast_bf16(h, ops.RESIDUAL_PRESCALE), p["ws"], bias=p["bs"])
         else:
             skip = h
         h2 = ops.conv3x3(n, p["w2"], dm.BT, dm.H, dm.W, bias=p["b2"], residual=skip)
@@ -800,11 +801,11 @@ class BasicTransformerBlock(_RefBindable, _Prepared):
         C = x.shape[1]
         if "cc_split" not in p:
             wf = self.cc_projection.weight.detach().float()
-            p["cc_split"] = (_bf16(wf[:, :C]), _bf16(wf[:, C:]))
+            p["cc_split"] = (_bf16(wf[:, :C] * (1.0 / ops.RESIDUAL_PRESCALE)), _bf16(wf[:, C:]))     # x operand stored pre-scaled (fp16 range)
         wx, wrt = p["cc_split"]
         rt = _pad_cols(_f32(cam.RT).view(dm.B * dm.T, -1), 16)
         rb = ops.skinny_linear(rt, _pad_cols(wrt, 16), b, False)                                    # [B*T, C]
-        return ops.linear(ops.cast_bf16(x), wx, rowbias=rb, rows_per_group=dm.HW)
+        return ops.linear(ops.cast_bf16(x, ops.RESIDUAL_PRESCALE), wx, rowbias=rb, rows_per_group=dm.HW)
 
     # ---- reference signature ----
     def forward(self, x, context=None, mask=None, camera_condition=None, **kwargs):
@@ -1249,7 +1250,7 @@ class UNetModel(_RefBindable, _Prepared):
         cam = self._camera_level(camera_condition, self.middle_ds, dm, dev, middle=True)
         h, dm = self.middle_block.forward_cl(h, emb, ctx, dm, cam)
         for i, module in enumerate(self.output_blocks):
-            hcat, hcat16 = ops.concat_channels(h, hs.pop(), True, True)
+            hcat, hcat16 = ops.concat_channels(h, hs.pop(), True, True, scale16=ops.RESIDUAL_PRESCALE)   # hcat16 feeds the skip conv only
             cam = self._camera_level(camera_condition, self.output_ds[i], dm, dev)
             h, dm = module.forward_cl(hcat, emb, ctx, dm, cam, hcat16)
         n = ops.groupnorm(h, p["g_out"], p["be_out"], dm.BT, dm.HW, 1e-5, True)

@@ -321,19 +321,28 @@ def from_channels_last(x: torch.Tensor, B: int, C_: int, S: int):
     return out
 
 
-def concat_channels(a: torch.Tensor, b: torch.Tensor, want_f32=True, want_bf16=False):
+# 16-bit copies of the UNNORMALISED fp32 residual stream (operand of the ResBlock 1x1 skip convolution) are stored at this power
+# of two and the convolution's packed weights carry the inverse: values up to 65504 / RESIDUAL_PRESCALE = 1.6e7 stay finite in the
+# IEEE-half build (an unscaled cast overflows at 65504), and the product is unchanged (both scalings are exact).
+RESIDUAL_PRESCALE = 2.0 ** -8
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor, want_f32=True, want_bf16=False, scale16: float = 1.0):
     rows, Ca = a.shape
     Cb = b.shape[1]
     of = torch.empty((rows, Ca + Cb), device=a.device, dtype=F32) if want_f32 else None
     ob = torch.empty((rows, Ca + Cb), device=a.device, dtype=BF16) if want_bf16 else None
-    _lib.call("c2v_concat_channels", _p(a), _p(b), _p(of), _p(ob), rows, Ca, Cb, _stream())
+    _lib.call("c2v_concat_channels_scaled", _p(a), _p(b), _p(of), _p(ob), rows, Ca, Cb, float(scale16), _stream())
     return of, ob
 
 
-def cast_bf16(x: torch.Tensor):
+def cast_bf16(x: torch.Tensor, scale: float = 1.0):
     _chk(x, F32, "cast_bf16.x")
     out = torch.empty(x.shape, device=x.device, dtype=BF16)
-    _lib.call("c2v_cast_bf16", _p(x), _p(out), x.numel(), _stream())
+    if scale == 1.0:
+        _lib.call("c2v_cast_bf16", _p(x), _p(out), x.numel(), _stream())
+    else:
+        _lib.call("c2v_cast_bf16_scaled", _p(x), _p(out), x.numel(), float(scale), _stream())
     return out
 
 

@@ -42,7 +42,8 @@ class ResnetBlock(nn.Module):
         p = dict(g1=_f32(self.norm1.weight), be1=_f32(self.norm1.bias), w1=w1, b1=b1, g2=_f32(self.norm2.weight), be2=_f32(self.norm2.bias),
                  w2=w2, b2=b2)
         if self.in_channels != self.out_channels:
-            p["ws"] = _bf16(self.nin_shortcut.weight.reshape(self.out_channels, self.in_channels))
+            # 16-bit copy of the unnormalised stream is stored at ops.RESIDUAL_PRESCALE, the weights carry the inverse (fp16 range)
+            p["ws"] = _bf16(self.nin_shortcut.weight.reshape(self.out_channels, self.in_channels) * (1.0 / ops.RESIDUAL_PRESCALE))
             p["bs"] = _f32(self.nin_shortcut.bias)
         return p
 
@@ -51,7 +52,7 @@ class ResnetBlock(nn.Module):
         n = ops.groupnorm(h, p["g1"], p["be1"], N, H * W, 1e-6, True)
         h1 = ops.conv3x3(n, p["w1"], N, H, W, bias=p["b1"])
         n = ops.groupnorm(h1, p["g2"], p["be2"], N, H * W, 1e-6, True)
-        skip = ops.linear(ops.cast_bf16(h), p["ws"], bias=p["bs"]) if "ws" in p else h
+        skip = ops.linear(ops.cast_bf16(h, ops.RESIDUAL_PRESCALE), p["ws"], bias=p["bs"]) if "ws" in p else h
         return ops.conv3x3(n, p["w2"], N, H, W, bias=p["b2"], residual=skip)
 
 

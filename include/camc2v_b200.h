@@ -196,6 +196,13 @@ int c2v_from_channels_last(const float* in, float* out, int B, int C, int S, voi
 int c2v_concat_channels(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, void* stream);
 /* fp32 -> bf16 cast of n elements. */
 int c2v_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+/* The same two with the 16-bit copy multiplied by `scale` (a power of two) first and, in the IEEE-half build, saturated at +-65504
+ * instead of overflowing to inf.  For 16-bit copies of UNNORMALISED data: the fp32 residual stream / skip concat that feeds the
+ * ResBlock's 1x1 skip convolution (R/lvdm/modules/networks/openaimodel3d.py:197-236 computes it in fp32 / autocast): the host stores
+ * the copy at 2^-8 and packs that convolution's weights at 2^8, so activations up to 1.6e7 stay finite and the product is unchanged. */
+int c2v_concat_channels_scaled(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, float scale16,
+                               void* stream);
+int c2v_cast_bf16_scaled(const float* in, void* out_bf16, int64_t n, float scale, void* stream);
 /* nearest 2x upsample (openaimodel3d.py:101-103) of channels-last fp32 [N,H,W,C] -> bf16 [N,2H,2W,C]. */
 int c2v_upsample2x(const float* in, void* out_bf16, int N, int H, int W, int C, void* stream);
 /* im2col for the stride-2 3x3 Downsample conv (openaimodel3d.py:68-70): fp32 [N,H,W,C] -> bf16 [N*(H/2)*(W/2), 9*C]. */

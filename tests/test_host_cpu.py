@@ -299,3 +299,62 @@ def test_product_package_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "oracle/" in src and f.endswith((".cu", ".cuh", ".h")) and "#include" in src and re.search(r'#include\s+"[^"]*oracle', src):
                     bad.append(f)
     assert bad == []
+
+
+def test_unmodified_reference_constructor_accepts_the_cuda_unet():
+    """INTEGRATION.md section 2 with NO other change: the reference's own CamContextI2V constructor, given
+    `unet_config.target: camc2v_b200.modules.UNetModel`, runs its by-name forward re-binding and Epipolar injection
+    (camcontexti2v.py:111-170) against this package's modules; the package declines the re-binding, adopts the injected modules
+    as its own classes, and the reference UNet's state_dict loads with strict=True."""
+    import os
+    import sys
+    import pytest
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    sys.path.insert(0, os.path.join(root, "oracle", "refgen"))
+    import ref_harness as rh
+    if not os.path.isdir(rh.REF_PKG):
+        pytest.skip("reference sources not available")
+    from camc2v_b200 import modules as M
+    small = dict(model_channels=64)
+    model = rh.build_reference_model(unet_overrides=small, unet_target="camc2v_b200.modules.UNetModel")
+    unet = model.model.diffusion_model
+    assert isinstance(unet, M.UNetModel)
+    assert unet.__dict__.get("_declined_rebinds") == ["new_forward_for_unet"]
+    assert type(unet).forward is M.UNetModel.forward and "forward" not in unet.__dict__
+    blocks = [b for b in unet.modules() if isinstance(b, M.BasicTransformerBlock) and hasattr(b, "epipolar")]
+    assert len(blocks) == 16 and all(isinstance(b.epipolar, M.Epipolar) and b.variant == "camcontext" for b in blocks)
+    assert all("forward" not in b.__dict__ and "_forward" not in b.__dict__ for b in blocks)
+    tts = [t for t in unet.modules() if isinstance(t, M.TemporalTransformer)]
+    assert all(t.__dict__.get("_declined_rebinds") == ["new_forward_for_TemporalTransformer"] for t in tts)
+    ref = rh.build_reference_model(unet_overrides=small)
+    res = unet.load_state_dict(ref.model.diffusion_model.state_dict(), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    # the model object the samplers talk to is the reference's own LatentDiffusion
+    assert type(model).__module__.startswith("model.") and hasattr(model, "apply_model") and model.parameterization == "eps"
+
+
+def test_sampler_rejects_unsupported_reference_options():
+    import pytest
+    import torch
+    from camc2v_b200.sampler import DDIMSampler
+
+    class Stub:
+        num_timesteps = 1000
+        parameterization = "eps"
+        use_dynamic_rescale = False
+        alphas_cumprod = torch.linspace(0.999, 0.01, 1000)
+        betas = torch.zeros(1000)
+
+    s = DDIMSampler(Stub())
+    s.make_schedule(25, "uniform_trailing", 1.0, verbose=False)
+    x = torch.zeros(1, 4, 16, 8, 8)
+    t = torch.zeros(1, dtype=torch.long)
+    for kw in (dict(mask=torch.ones(1)), dict(x0=x), dict(paste_cond_frame=True), dict(noise_shaping=True), dict(timesteps=10),
+               dict(precision=16), dict(quantize_denoised=True), dict(score_corrector=object())):
+        with pytest.raises(NotImplementedError):
+            s.p_sample_ddim(x, {}, t, index=0, **kw)
+    with pytest.raises(NotImplementedError):
+        s.sample(25, 1, (4, 16, 8, 8), mask=torch.ones(1))
+    Stub.parameterization = "v"
+    with pytest.raises(NotImplementedError):
+        DDIMSampler(Stub())
