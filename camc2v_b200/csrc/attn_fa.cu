@@ -55,7 +55,15 @@ constexpr int FA_D = 64;
 #define FA_T(i) do { } while (0)
 #endif
 constexpr int FA_KV_STAGES = C2V_FA_KV_STAGES;
-constexpr int FA_THREADS = 192;
+// threads per query row: 2 = each of the two 32-key halves of a tile has its own warp (8 softmax warps, 4 per SM sub-partition with
+// two CTAs per SM: the softmax is MUFU / latency bound, so the extra warps are what keeps the exp2 pipe busy); 1 = one thread per row
+// processes both halves one after the other (4 softmax warps)
+#ifndef C2V_FA_SPLIT
+#define C2V_FA_SPLIT 2
+#endif
+#define FA_SPLIT C2V_FA_SPLIT
+constexpr int FA_NH = 2 / FA_SPLIT;                  // key halves per thread
+constexpr int FA_THREADS = 64 + 128 * FA_SPLIT;
 constexpr float FA_TAU = 8.0f;                       // lazy-rescale threshold (log2 units): P <= 2^8
 
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;         // 16 KB
@@ -67,11 +75,11 @@ constexpr int FA_OFF_V = FA_OFF_K + FA_KV_STAGES * FA_K_BYTES;
 constexpr int FA_OFF_BAR = FA_OFF_V + FA_KV_STAGES * FA_V_BYTES;
 constexpr int FA_OFF_LIST = FA_OFF_BAR + 256;
 constexpr int FA_MAX_TILES = 1024;
-constexpr int FA_SMEM = FA_OFF_LIST + FA_MAX_TILES * 2;
+constexpr int FA_OFF_XCH = FA_OFF_LIST + FA_MAX_TILES * 2;       // (m, l) of the two streams of a row, exchanged once in the epilogue
+constexpr int FA_SMEM = FA_OFF_XCH + 2 * FA_BM * 8;
 
-constexpr uint32_t FA_TM_S = 0;                      // S buffers: 2 x 64 fp32 columns
-constexpr uint32_t FA_TM_O = 2 * FA_BN;              // O accumulator: 64 columns
-constexpr uint32_t FA_TM_P = FA_TM_O + FA_D;         // P buffers: 2 x 32 columns (64 keys as 16-bit pairs)
+constexpr uint32_t FA_TM_S = 0;                      // S buffers: 2 x 64 fp32 columns; P_h(j) = first 16 columns of chunk h of S(j)
+constexpr uint32_t FA_TM_O = 2 * FA_BN;              // O accumulators of the two key-half streams: 2 x 64 columns
 constexpr uint32_t FA_TMEM_COLS = 256;
 
 constexpr uint32_t FA_NEG_INF = 0xff800000u;
@@ -144,12 +152,12 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
     uint64_t* q_full = bars + 0;
     uint64_t* kv_full = bars + 1;     // [FA_KV_STAGES <= 4]
     uint64_t* kv_empty = bars + 5;    // [FA_KV_STAGES <= 4]
-    uint64_t* s_full = bars + 9;      // [2]  S(j) is in TMEM buffer j & 1
-    uint64_t* p_full = bars + 11;     // [2]  P(j) has been stored over S(j)
-    uint64_t* pv_done = bars + 13;    // one phase per PV(j)
-    uint64_t* o_final = bars + 14;    // the last PV
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
-    int* n_act_s = reinterpret_cast<int*>(bars + 16);
+    uint64_t* s_full = bars + 9;      // [2]     S(j) is in TMEM buffer j & 1
+    uint64_t* p_full = bars + 11;     // [2][2]  P_h(j) has been stored over chunk h of S(j): index (j & 1) * 2 + h
+    uint64_t* pv_done = bars + 15;    // [2]     one phase per PV_h(j)
+    uint64_t* o_final = bars + 17;    // the last PV
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+    int* n_act_s = reinterpret_cast<int*>(bars + 19);
 
     const int warp = threadIdx.x >> 5;
     // CTA -> (query tile, head); with an epipolar tile map the CTAs are issued heaviest query tile first (see attn_tc.cu)
@@ -184,9 +192,9 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], C2V_FA_WARP_ARRIVE ? 4 : 128);
+            mbar_init(&pv_done[i], 1);
         }
-        mbar_init(pv_done, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);      // one elected lane of each of the 4 warps that own a chunk
         mbar_init(o_final, 1);
         fence_barrier_init();
     }
@@ -260,33 +268,41 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
             if (n_act > 1) issue_qk(1);
             for (int j = 0; j < n_act; ++j) {
                 const int s = j % FA_KV_STAGES;
-                mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t v_addr = smem_u32(smem + FA_OFF_V + s * FA_V_BYTES);
-                    const uint32_t p_tmem = tmem_base + FA_TM_P + (uint32_t)(j & 1) * (FA_BN / 2);
 #pragma unroll
-                    for (int ks = 0; ks < FA_BN / 16; ++ks) {
-                        const uint64_t vd = umma_desc_sw128(v_addr + ks * 16 * 128);
-                        umma_bf16_ts(tmem_base + FA_TM_O, p_tmem + ks * 8, vd, idesc_pv, (j | ks) != 0);
+                for (int h = 0; h < 2; ++h) {             // the two 32-key halves are independent streams with their own accumulator
+                    mbar_wait(&p_full[(j & 1) * 2 + h], (j >> 1) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t v_addr = smem_u32(smem + FA_OFF_V + s * FA_V_BYTES) + h * 32 * 128;
+                        const uint32_t p_tmem = tmem_base + FA_TM_S + (uint32_t)(j & 1) * FA_BN + h * 32;
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t vd = umma_desc_sw128(v_addr + ks * 16 * 128);
+                            umma_bf16_ts(tmem_base + FA_TM_O + h * FA_D, p_tmem + ks * 8, vd, idesc_pv, (j | ks) != 0);
+                        }
+                        umma_commit(&pv_done[h]);
+                        if (h == 1) {
+                            umma_commit(&kv_empty[s]);
+                            if (j == n_act - 1) umma_commit(o_final);
+                        }
                     }
-                    umma_commit(&kv_empty[s]);
-                    umma_commit(pv_done);
-                    if (j == n_act - 1) umma_commit(o_final);
+                    __syncwarp();
                 }
-                __syncwarp();
                 // the tensor pipe executes this thread's MMAs in issue order: QK(j+2) may overwrite buffer j & 1 (= P(j)) now
                 if (j + 2 < n_act) issue_qk(j + 2);
             }
         }
     } else {
-        // ===================== softmax / rescale / epilogue (warps 2..5) =====================
+        // ===================== softmax / rescale / epilogue (warps 2 .. 2 + 4 * FA_SPLIT) =====================
+        // TMEM lane quarter lg (a warp may only touch lanes 32 * (warp % 4) ..), row r of the query tile; with FA_SPLIT = 2 the
+        // warp pair (w, w + 4) shares rows and each warp owns one 32-key half of every tile.
         const int lg = warp & 3;
+        const int half0 = (warp - 2) >> 2;                         // first (only, if FA_SPLIT == 2) half this thread processes
         const int r = lg * 32 + lane_id();
         const int qi = q0 + r;                                     // query index inside the batch
-        const uint32_t t_s0 = tmem_base + FA_TM_S + ((uint32_t)(lg * 32) << 16);
-        const uint32_t t_o = tmem_base + FA_TM_O + ((uint32_t)(lg * 32) << 16);
-        const uint32_t t_p0 = tmem_base + FA_TM_P + ((uint32_t)(lg * 32) << 16);
+        const uint32_t t_lane = (uint32_t)(lg * 32) << 16;
+        const uint32_t t_s0 = tmem_base + FA_TM_S + t_lane;
+        const uint32_t t_o0 = tmem_base + FA_TM_O + t_lane;
         const bool epi = p.epi_F != nullptr;
         const bool use_words = MODE == 0 && epi && p.bitmask != nullptr;
         const unsigned char* mrow = (MODE == 1 && p.mask) ? p.mask + (size_t)b * p.mask_bstride + (size_t)min(qi, p.lq - 1) * p.lk : nullptr;
@@ -306,195 +322,149 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
         float thr_m = 0.f;
         float l0x[MODE == 2 ? (1 << LOGW) : 1];
 
-        float m_ref = -INFINITY;   // reference maximum of the exponentials (log2 domain), raised lazily
-        float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // running row sum, four independent partial sums
-
+        // Per stream (key half h of every tile): reference maximum of the exponentials (log2 domain, raised lazily) and row sum.
+        float m_ref[FA_NH], l_sum[FA_NH];
+#pragma unroll
+        for (int i = 0; i < FA_NH; ++i) {
+            m_ref[i] = -INFINITY;
+            l_sum[i] = 0.f;
+        }
         const uint32_t* wbase = use_words ? p.bitmask + ((size_t)b * gridDim.x + q_tile) * (size_t)(p.lk >> 5) * FA_BM + r : nullptr;
-        uint32_t bw_n[2] = {0u, 0u};                       // packed mask words fetched one tile ahead of their use
-        auto fetch_words = [&](int jt_, uint32_t (&w)[2]) {
-            if (jt_ < n_main) {
-                const uint32_t* q = wbase + (size_t)jt_ * 2 * FA_BM;
-                w[0] = __ldg(q);
-                w[1] = __ldg(q + FA_BM);
-            }
-        };
-        // Mask words of this row for the two 32-key chunks of visited tile `it` (bit i = key (chunk base + i) is attended) and
-        // the warp-uniform flags derived from them: act = some row of the warp attends a key of the chunk (else the chunk is never
-        // read, its probabilities are stored as zeros), full = no row masks anything (the select is skipped).
-        struct TileInfo {
-            uint32_t w0, w1;
-            bool act0, act1, full0, full1;
-        };
-        auto tile_info = [&](int it) -> TileInfo {
-            const int jt = tile_list[it];
+
+        // Mask word of this row for 32-key chunk c of key tile jt: bit i = key (chunk base + i) is attended.
+        auto chunk_word = [&](int jt, int c) -> uint32_t {
             const bool main_seg = jt < n_main;
             const int klim = main_seg ? p.lk : p.lk2;
-            const int tile_key0 = main_seg ? jt * FA_BN : 0;
-            TileInfo ti;
-            if (!(main_seg && (epi || mrow)) && tile_key0 + FA_BN <= klim) {      // dense tile, fully inside the sequence: no votes
-                ti.w0 = ti.w1 = 0xffffffffu;
-                ti.act0 = ti.act1 = ti.full0 = ti.full1 = true;
-                return ti;
-            }
-            uint32_t bw[2];
-            // ---- mask words of this row for the tile's two 32-key chunks: bit i = key (chunk base + i) is attended ----
-            if (use_words && main_seg) {
-                bw[0] = bw_n[0];
-                bw[1] = bw_n[1];
-            } else if (MODE == 2 && epi && main_seg) {
+            const int key0 = (main_seg ? jt * FA_BN : 0) + c * 32;
+            if (use_words && main_seg) return __ldg(wbase + ((size_t)jt * 2 + c) * FA_BM);
+            if (MODE == 2 && epi && main_seg) {
                 constexpr int W = 1 << (MODE == 2 ? LOGW : 5);
                 constexpr int RPC = 32 / W;
                 constexpr float DF = (float)D, OFFC = (float)D * 0.5f - 0.5f;
+                const int t2 = key0 >> (2 * LOGW);
+                if (t2 != cur_t2) {                     // warp-uniform: once per key frame
+                    cur_t2 = t2;
+                    line = fa_epi_line(Frow + t2 * 9, xi, yi);
+                    const float cmax = (float)(W - 1) * DF + OFFC;
+                    thr_m = p.epi_thr + 1e-6f + 4e-7f * (fabsf(line.l0) * cmax + fabsf(line.l1) * cmax + fabsf(line.l2));
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int key0 = tile_key0 + c * 32;
-                    const int t2 = key0 >> (2 * LOGW);
-                    if (t2 != cur_t2) {                     // warp-uniform: once per key frame
-                        cur_t2 = t2;
-                        line = fa_epi_line(Frow + t2 * 9, xi, yi);
-                        const float cmax = (float)(W - 1) * DF + OFFC;
-                        thr_m = p.epi_thr + 1e-6f + 4e-7f * (fabsf(line.l0) * cmax + fabsf(line.l1) * cmax + fabsf(line.l2));
-#pragma unroll
-                        for (int x = 0; x < W; ++x) l0x[x] = __fmul_rn(line.l0, (float)x * DF + OFFC);
-                    }
-                    const int py0 = (key0 & (W * W - 1)) >> LOGW;
-                    float yr[RPC];
-                    bool maybe = false;
-#pragma unroll
-                    for (int rr = 0; rr < RPC; ++rr) {
-                        yr[rr] = (float)(py0 + rr) * DF + OFFC;
-                        const float w0 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, OFFC)), line.l2);
-                        const float w1 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, (float)(W - 1) * DF + OFFC)), line.l2);
-                        maybe |= !((w0 > thr_m && w1 > thr_m) || (w0 < -thr_m && w1 < -thr_m));
-                    }
-                    uint32_t word = 0;
-                    if (maybe) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float wv = __fadd_rn(__fmaf_rn(line.l1, yr[i >> LOGW], l0x[i & (W - 1)]), line.l2);
-                            word |= (fabsf(wv) < p.epi_thr ? 1u : 0u) << i;
-                        }
-                    }
-                    bw[c] = word;
+                    for (int x = 0; x < W; ++x) l0x[x] = __fmul_rn(line.l0, (float)x * DF + OFFC);
                 }
-            } else if (MODE == 1 && main_seg && mrow) {
+                const int py0 = (key0 & (W * W - 1)) >> LOGW;
+                float yr[RPC];
+                bool maybe = false;
+#pragma unroll
+                for (int rr = 0; rr < RPC; ++rr) {
+                    yr[rr] = (float)(py0 + rr) * DF + OFFC;
+                    // the distance is linear in x: both row ends beyond threshold + margin on the same side => no key of the row passes
+                    const float w0 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, OFFC)), line.l2);
+                    const float w1 = __fadd_rn(__fmaf_rn(line.l1, yr[rr], __fmul_rn(line.l0, (float)(W - 1) * DF + OFFC)), line.l2);
+                    maybe |= !((w0 > thr_m && w1 > thr_m) || (w0 < -thr_m && w1 < -thr_m));
+                }
+                uint32_t word = 0;
+                if (maybe) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float wv = __fadd_rn(__fmaf_rn(line.l1, yr[i >> LOGW], l0x[i & (W - 1)]), line.l2);
+                        word |= (fabsf(wv) < p.epi_thr ? 1u : 0u) << i;
+                    }
+                }
+                return word;
+            }
+            if (MODE == 1 && main_seg && mrow) {
                 // materialised byte mask (reference format, bool / uint8 [B, lq, lk]): 32 bytes -> one word
+                uint32_t word = 0;
+                if (key0 + 32 <= p.lk && (p.lk & 15) == 0) {
+                    const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + key0);
+                    const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + key0 + 16);
+                    const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int key0 = tile_key0 + c * 32;
-                    uint32_t word = 0;
-                    if (key0 + 32 <= p.lk && (p.lk & 15) == 0) {
-                        const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + key0);
-                        const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + key0 + 16);
-                        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-                        for (int w8 = 0; w8 < 8; ++w8)      // non-zero byte -> bit: 0xFF per byte, top bits gathered by a multiply
-                            word |= (((((__vcmpne4(mw[w8], 0u) >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * w8);
-                    } else {
-#pragma unroll 1
-                        for (int i = 0; i < 32; ++i) {
-                            const int key = key0 + i;
-                            word |= ((key < klim && mrow[key] != 0) ? 1u : 0u) << i;
-                        }
-                    }
-                    bw[c] = word;
-                }
-            } else if (MODE == 1 && main_seg && epi) {
-                // exact predicate on an arbitrary grid (non power-of-two, or a chunk spanning several frames): rolled loop
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int key0 = tile_key0 + c * 32;
-                    uint32_t word = 0;
+                    for (int w8 = 0; w8 < 8; ++w8)      // non-zero byte -> bit: 0xFF per byte, top bits gathered by a multiply
+                        word |= (((((__vcmpne4(mw[w8], 0u) >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * w8);
+                } else {
 #pragma unroll 1
                     for (int i = 0; i < 32; ++i) {
                         const int key = key0 + i;
-                        bool ok = key < klim;
-                        if (ok) {
-                            const int t2 = key / HW;
-                            if (t2 != cur_t2) {
-                                cur_t2 = t2;
-                                line = fa_epi_line(Frow + t2 * 9, xi, yi);
-                            }
-                            const int pj = key - t2 * HW;
-                            const float xj = __fadd_rn(__fmul_rn((float)(pj % p.epi_W), (float)p.epi_d), p.epi_off);
-                            const float yj = __fadd_rn(__fmul_rn((float)(pj / p.epi_W), (float)p.epi_d), p.epi_off);
-                            const float dist = fabsf(__fadd_rn(__fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj)), line.l2));
-                            ok = dist < p.epi_thr;
-                        }
-                        word |= (ok ? 1u : 0u) << i;
+                        word |= ((key < klim && mrow[key] != 0) ? 1u : 0u) << i;
                     }
-                    bw[c] = word;
                 }
-            } else {
-                // dense keys (and the never-masked register-token segment): everything below klim
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int nv = klim - (tile_key0 + c * 32);
-                    bw[c] = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
-                }
+                return word;
             }
-            ti.w0 = bw[0];
-            ti.w1 = bw[1];
-            ti.act0 = __any_sync(0xffffffffu, bw[0] != 0u);
-            ti.act1 = __any_sync(0xffffffffu, bw[1] != 0u);
-            ti.full0 = __all_sync(0xffffffffu, bw[0] == 0xffffffffu);
-            ti.full1 = __all_sync(0xffffffffu, bw[1] == 0xffffffffu);
-            return ti;
+            if (MODE == 1 && main_seg && epi) {
+                // exact predicate on an arbitrary grid (non power-of-two, or a chunk spanning several frames): rolled loop
+                uint32_t word = 0;
+#pragma unroll 1
+                for (int i = 0; i < 32; ++i) {
+                    const int key = key0 + i;
+                    bool ok = key < klim;
+                    if (ok) {
+                        const int t2 = key / HW;
+                        if (t2 != cur_t2) {
+                            cur_t2 = t2;
+                            line = fa_epi_line(Frow + t2 * 9, xi, yi);
+                        }
+                        const int pj = key - t2 * HW;
+                        const float xj = __fadd_rn(__fmul_rn((float)(pj % p.epi_W), (float)p.epi_d), p.epi_off);
+                        const float yj = __fadd_rn(__fmul_rn((float)(pj / p.epi_W), (float)p.epi_d), p.epi_off);
+                        const float dist = fabsf(__fadd_rn(__fmaf_rn(line.l1, yj, __fmul_rn(line.l0, xj)), line.l2));
+                        ok = dist < p.epi_thr;
+                    }
+                    word |= (ok ? 1u : 0u) << i;
+                }
+                return word;
+            }
+            // dense keys (and the never-masked register-token segment): everything below klim
+            const int nv = klim - key0;
+            return nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+        };
+        // true when chunk_word is the all-ones constant for every row (dense tile fully inside the sequence): no load, no votes
+        auto chunk_dense = [&](int jt, int c) -> bool {
+            const bool main_seg = jt < n_main;
+            return !(main_seg && (epi || mrow)) && (main_seg ? jt * FA_BN : 0) + c * 32 + 32 <= (main_seg ? p.lk : p.lk2);
         };
 
-        // O *= alpha (rows of this thread): only on the rare tiles where the reference maximum is raised
-        auto rescale_o = [&](float alpha) {
-            tmem_st_wait();                                           // an earlier rescale of the same tile may still be in flight
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t o[16];
-                tmem_ld16(t_o + c * 16, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st16(t_o + c * 16, o);
-            }
-        };
-        // One 32-key chunk: mask -> max -> (rarely) raise the reference maximum -> exp2 -> 16-bit pairs -> TMEM columns t_pc..+16.
-        // `fix_p0`: TMEM address of the chunk-0 probabilities of the same tile, already stored under the old reference (0 if none).
-        auto chunk = [&](uint32_t (&v)[32], uint32_t word, bool act, bool full, uint32_t t_pc, int j, uint32_t fix_p0) {
+        // One 32-key chunk of one stream: S columns -> mask -> max -> (rarely) raise the reference maximum and rescale this stream's
+        // O accumulator -> exp2 -> 16-bit pairs stored over the first 16 of the 32 S columns just read.
+        auto chunk = [&](int j, int h, int hi, uint32_t word, bool dense) {
+            const uint32_t t_sc = t_s0 + (uint32_t)(j & 1) * FA_BN + h * 32;
             uint32_t w[16];
-            if (!act) {
+            const bool act = dense || __any_sync(0xffffffffu, word != 0u);
+            if (!act) {                                               // no row of this warp attends a key of the chunk
 #pragma unroll
                 for (int i = 0; i < 16; ++i) w[i] = 0u;
-                tmem_st16(t_pc, w);
+                tmem_st16(t_sc, w);
                 return;
             }
-            if (!full) {
+            uint32_t v[32];
+            tmem_ld32(t_sc, v);
+            tmem_ld_wait();
+            if (!dense && !__all_sync(0xffffffffu, word == 0xffffffffu)) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = (word >> i) & 1u ? v[i] : FA_NEG_INF;
             }
             const float mt = fa_max32(v) * p.scale_log2;               // scale > 0; -inf stays -inf
-            if (__any_sync(0xffffffffu, mt > m_ref + FA_TAU)) {       // first attended key of a row: m_ref = -inf -> true
-                const float m_new = fmaxf(m_ref, mt);
-                const float alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_new);
-                l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
-                m_ref = m_new;
-                if (j > 0) {                                          // O holds PV(0..j-1): wait for PV(j-1), rescale in place
-                    mbar_wait(pv_done, (j - 1) & 1);
+            if (__any_sync(0xffffffffu, mt > m_ref[hi] + FA_TAU)) {   // first attended key of a row: m_ref = -inf -> true
+                const float m_new = fmaxf(m_ref[hi], mt);
+                const float alpha = (m_ref[hi] == -INFINITY) ? 0.f : fast_exp2(m_ref[hi] - m_new);
+                l_sum[hi] *= alpha;
+                m_ref[hi] = m_new;
+                if (j > 0) {                                          // O_h holds PV_h(0..j-1): wait for PV_h(j-1), rescale in place
+                    mbar_wait(&pv_done[h], (j - 1) & 1);
                     tc_fence_after();
-                    rescale_o(alpha);
-                }
-                if (fix_p0) {                                         // chunk 0 of this tile was stored under the old reference
-                    uint32_t q[16];
-                    tmem_st_wait();
-                    tmem_ld16(fix_p0, q);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[i]));
-                        q[i] = pack_bf16(f.x * alpha, f.y * alpha);
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t o[16];
+                        tmem_ld16(t_o0 + h * FA_D + c * 16, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st16(t_o0 + h * FA_D + c * 16, o);
                     }
-                    tmem_st16(fix_p0, q);
                 }
             }
-            const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+            const float m_use = (m_ref[hi] == -INFINITY) ? 0.f : m_ref[hi];
             const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
+            float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float2 x = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
@@ -504,11 +474,12 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
                 const bool px = pos < NP, py = pos + 1 < NP;
                 e.x = px ? (v[2 * i] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.x)) : fast_exp2(x.x);
                 e.y = py ? (v[2 * i + 1] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.y)) : fast_exp2(x.y);
-                if (i & 1) l2b = fadd2(l2b, e);
-                else l2a = fadd2(l2a, e);
+                if (i & 1) lb = fadd2(lb, e);
+                else la = fadd2(la, e);
                 w[i] = pack_bf16(e.x, e.y);
             }
-            tmem_st16(t_pc, w);
+            l_sum[hi] += (la.x + la.y) + (lb.x + lb.y);
+            tmem_st16(t_sc, w);
         };
 
 #if C2V_FA_TIMING
@@ -516,85 +487,97 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
         long long tlast = clock64();
         const long long tstart = tlast;
 #endif
-        // Software pipeline over half tiles: while chunk 0 of tile j is processed the load of chunk 1 is in flight, and while chunk 1
-        // is processed the load of chunk 0 of tile j+1 is (v0 is dead by then), so neither the tcgen05.ld latency nor the wait for
-        // S(j+1) sits on the warp's critical path.
-        uint32_t v0[32], v1[32];
-        TileInfo ti = {0u, 0u, false, false, false, false};
-        if (n_act > 0) {
-            if (use_words) fetch_words(tile_list[0], bw_n);
-            ti = tile_info(0);
-            if (use_words && n_act > 1) fetch_words(tile_list[1], bw_n);
-            mbar_wait(&s_full[0], 0);
-            tc_fence_after();
-            if (ti.act0) tmem_ld32(t_s0, v0);
-        }
+        // mask words one tile ahead of their use (global loads of the packed mask)
+        uint32_t wnext[FA_NH];
+        bool dnext[FA_NH];
+        auto fetch = [&](int it) {
+            const int jt = tile_list[it];
+#pragma unroll
+            for (int hi = 0; hi < FA_NH; ++hi) {
+                dnext[hi] = chunk_dense(jt, half0 + hi);
+                wnext[hi] = dnext[hi] ? 0xffffffffu : chunk_word(jt, half0 + hi);
+            }
+        };
+        if (n_act > 0) fetch(0);
         for (int j = 0; j < n_act; ++j) {
-            const uint32_t t_s = t_s0 + (uint32_t)(j & 1) * FA_BN;
-            const uint32_t t_p = t_p0 + (uint32_t)(j & 1) * (FA_BN / 2);
-            tmem_ld_wait();                                           // v0 = S(j) chunk 0
-            if (ti.act1) tmem_ld32(t_s + 32, v1);
+            uint32_t wcur[FA_NH];
+            bool dcur[FA_NH];
+#pragma unroll
+            for (int hi = 0; hi < FA_NH; ++hi) {
+                wcur[hi] = wnext[hi];
+                dcur[hi] = dnext[hi];
+            }
+            if (j + 1 < n_act) fetch(j + 1);
             FA_T(0);
-            chunk(v0, ti.w0, ti.act0, ti.full0, t_p, j, 0u);
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
             FA_T(1);
-            TileInfo tn = ti;
-            if (j + 1 < n_act) {
-                tn = tile_info(j + 1);                                // consumes bw_n
-                if (use_words && j + 2 < n_act) fetch_words(tile_list[j + 2], bw_n);
+#pragma unroll
+            for (int hi = 0; hi < FA_NH; ++hi) {
+                const int h = half0 + hi;
+                chunk(j, h, hi, wcur[hi], dcur[hi]);
+                FA_T(2 + hi);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane_id() == 0) mbar_arrive(&p_full[(j & 1) * 2 + h]);
             }
-            FA_T(2);
-            tmem_ld_wait();                                           // v1 = S(j) chunk 1
-            if (j + 1 < n_act) {
-                mbar_wait(&s_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                tc_fence_after();
-                if (tn.act0) tmem_ld32(t_s0 + (uint32_t)((j + 1) & 1) * FA_BN, v0);
-            }
-            FA_T(3);
-            chunk(v1, ti.w1, ti.act1, ti.full1, t_p + 16, j, ti.act0 ? t_p : 0u);
             FA_T(4);
-            tmem_st_wait();
-            tc_fence_before();
-#if C2V_FA_WARP_ARRIVE
-            __syncwarp();
-            if (lane_id() == 0) mbar_arrive(&p_full[j & 1]);
-#else
-            mbar_arrive(&p_full[j & 1]);
-#endif
-            ti = tn;
-            FA_T(5);
         }
-        const float l_run = (l2a.x + l2a.y) + (l2b.x + l2b.y);
 #if C2V_FA_TIMING
         if (lane_id() == 0 && warp == 2 && blockIdx.y == 0 && blockIdx.z == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
-            printf("fa_timing cta %d tiles %d cycles/tile: ld1+wait %lld chunk0 %lld info %lld waitS+ld %lld chunk1 %lld store %lld | total %lld\n",
-                   blockIdx.x, n_act, tacc[0] / n_act, tacc[1] / n_act, tacc[2] / n_act, tacc[3] / n_act, tacc[4] / n_act, tacc[5] / n_act,
-                   (clock64() - tstart) / n_act);
+            printf("fa_timing cta %d tiles %d cycles/tile: fetch %lld waitS %lld chunkA %lld chunkB %lld arrive %lld | total %lld\n", blockIdx.x,
+                   n_act, tacc[0] / n_act, tacc[1] / n_act, tacc[2] / n_act, tacc[3] / n_act, tacc[4] / n_act, (clock64() - tstart) / n_act);
 #endif
-        // ---- epilogue: O / l -> 16-bit -> global ----
+        // ---- epilogue: merge the two streams (different reference maxima), normalise, 16-bit -> global ----
+        // out = (a0 O_0 + a1 O_1) / (a0 l_0 + a1 l_1), a_h = 2^(m_h - max(m_0, m_1)); this thread writes head-dim columns
+        // [ocol0, ocol0 + FA_OCOLS) of its row.
+        float mm[2], ll[2];
+#if FA_SPLIT == 2
+        float2* xch = reinterpret_cast<float2*>(smem + FA_OFF_XCH);
+        xch[half0 * FA_BM + r] = make_float2(m_ref[0], l_sum[0]);
+        named_bar_sync(1 + lg, 64);                                   // the warp pair that shares these rows
+        const float2 oth = xch[(half0 ^ 1) * FA_BM + r];
+        mm[half0] = m_ref[0];
+        ll[half0] = l_sum[0];
+        mm[half0 ^ 1] = oth.x;
+        ll[half0 ^ 1] = oth.y;
+#else
+        mm[0] = m_ref[0]; ll[0] = l_sum[0]; mm[1] = m_ref[1]; ll[1] = l_sum[1];
+#endif
+        const float mmax = fmaxf(mm[0], mm[1]);
+        const float a0 = (mm[0] == -INFINITY) ? 0.f : fast_exp2(mm[0] - mmax);
+        const float a1 = (mm[1] == -INFINITY) ? 0.f : fast_exp2(mm[1] - mmax);
+        const float l_run = a0 * ll[0] + a1 * ll[1];
         if (n_act > 0) {
             mbar_wait(o_final, 0);
             tc_fence_after();
         }
         const float inv = (l_run > 1e-30f && n_act > 0) ? p.out_scale / l_run : 0.f;
+        const float s0 = a0 * inv, s1 = a1 * inv;
         const bool row_ok = qi < p.lq;
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)b * p.o_bstride + (size_t)qi * p.ldo + head * FA_D;
+        constexpr int FA_OCOLS = FA_D / FA_SPLIT;
+        const int ocol0 = (FA_SPLIT == 2 ? half0 : 0) * FA_OCOLS;
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)b * p.o_bstride + (size_t)qi * p.ldo + head * FA_D + ocol0;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
+        for (int c = 0; c < FA_OCOLS / 16; ++c) {
+            uint32_t oa[16], ob[16];
             if (n_act > 0) {
-                tmem_ld32(t_o + c * 32, o);
+                tmem_ld16(t_o0 + ocol0 + c * 16, oa);
+                tmem_ld16(t_o0 + FA_D + ocol0 + c * 16, ob);
                 tmem_ld_wait();
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = 0u;
+                for (int i = 0; i < 16; ++i) oa[i] = ob[i] = 0u;
             }
             if (row_ok) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
+                for (int i = 0; i < 16; i += 8) {
                     float f[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = inv != 0.f ? __uint_as_float(o[i + e]) * inv : 0.f;
-                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32 + i);
+                    for (int e = 0; e < 8; ++e)
+                        f[e] = inv != 0.f ? __uint_as_float(oa[i + e]) * s0 + __uint_as_float(ob[i + e]) * s1 : 0.f;
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 16 + i);
                     if (p.accumulate) {
                         const uint4 prev = *dst;
                         const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
