@@ -4,7 +4,7 @@
 #include <stdlib.h>
 
 #include "../../include/camc2v_b200.h"
-#include "attn_tc.h"
+#include "attn.h"
 #include "common.cuh"
 #include "gemm_tc.h"
 #include "kernels.h"
@@ -101,14 +101,8 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     if (a.splits > 1) {
         if (d->epi != C2V_EPI_LINEAR || a.splits > a.taps * a.k_chunks) return ERR_BAD_ARG;
         if (a.splits > 8) return ERR_UNSUPPORTED;
-        if (!d->ws) {
-            // no workspace: the splits of a tile run as one thread-block cluster (<= 8 CTAs) and reduce through DSMEM
-            if (a.splits > 8 || d->ldo % 4 != 0 || (d->residual && d->ldr % 4 != 0)) return ERR_UNSUPPORTED;
-            if ((reinterpret_cast<uintptr_t>(d->out) & 15) != 0 && !d->out_bf16) return ERR_UNSUPPORTED;
-            a.cluster_reduce = 1;
-        } else {
-            a.out = d->ws;
-        }
+        if (!d->ws) return ERR_BAD_ARG;          // split-K needs the caller's fp32 workspace [splitk, M, N]
+        a.out = d->ws;
     }
 
     if (d->a_mode == C2V_A_PLAIN) {
@@ -177,7 +171,7 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
         const uint32_t box[2] = {64, (uint32_t)bn};
         if (!make_tmap_bf16(&a.tmB, d->w, 2, dims, strides, box)) return ERR_TMA_ENCODE;
     }
-    if (d->epi != C2V_EPI_GEGLU && !a.cluster_reduce) {
+    if (d->epi != C2V_EPI_GEGLU) {
         // TMA epilogue descriptors (residual load, output / split-K partial store).  When the output rows are not 16-byte
         // aligned (e.g. a 4-column bf16 output) the kernel falls back to its direct-store epilogue.
         const bool part = a.splits > 1;
@@ -208,7 +202,7 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     const int n_tiles = (d->N + bn - 1) / bn;
     if (n_tiles > 65535) return ERR_UNSUPPORTED;
     const int rc = gemm_tc_launch(a, bn, m_tiles, n_tiles, (cudaStream_t)stream);
-    if (rc != OK || a.splits == 1 || a.cluster_reduce) return rc;
+    if (rc != OK || a.splits == 1) return rc;
     return splitk_reduce_launch(d->ws, a.splits, d->M, d->N, d->bias, d->rowbias, a.rows_per_group, d->residual, d->ldr, d->out, d->ldo,
                                 d->out_bf16, (cudaStream_t)stream);
 }
@@ -311,12 +305,6 @@ int c2v_attention(const c2v_attn_desc* d, void* stream) {
         a.tile_map_words = c2v_epipolar_tile_map_words(d->epi_T, d->epi_H, d->epi_W);
     }
     if (d->epi_bitmask && d->epi_F && d->lq % 128 == 0) a.bitmask = d->epi_bitmask;
-    // C2V_ATTN_IMPL=tc selects the round-1 two-pass pipeline (attn_tc.cu) for A/B measurements; default: attn_fa.cu
-    static const bool use_tc = [] {
-        const char* e = getenv("C2V_ATTN_IMPL");
-        return e && e[0] == 't';
-    }();
-    if (use_tc) return attn_tc_launch(a, (d->lq + 127) / 128, d->heads, d->bq, (cudaStream_t)stream);
     return attn_fa_launch(a, (d->lq + 127) / 128, d->heads, d->bq, (cudaStream_t)stream);
 }
 

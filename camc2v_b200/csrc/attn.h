@@ -1,4 +1,4 @@
-// Kernel-side argument block of the tcgen05 flash attention (attn_tc.cu).
+// Kernel-side argument block of the tcgen05 flash attention (attn_fa.cu) and launchers of the attention family.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -30,8 +30,7 @@ struct AttnKernelArgs {
     float epi_thr, epi_off;      // float32(d*sqrt(2)/2), d/2 - 0.5
 };
 
-int attn_tc_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st);
-// attn_fa.cu: the round-2 pipeline (single-pass softmax, lazy rescale, P kept in tensor memory, PV as a TMEM-operand MMA)
+// attn_fa.cu: single-pass softmax in two key-half streams, lazy rescale, P kept in tensor memory, PV as a TMEM-operand MMA
 int attn_fa_launch(const AttnKernelArgs& a, int q_tiles, int heads, int batch, cudaStream_t st);
 // attn_small.cu: dense attention with lk <= 256 on warp-level tensor cores (all of K / V resident in shared memory)
 int attn_small_launch(const void* q, const void* k, const void* v, void* out, int bq, int lq, int lk, int heads, int kv_div, int ldq, int ldk,

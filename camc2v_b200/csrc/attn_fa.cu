@@ -1,29 +1,37 @@
-// Single-pass flash attention on tcgen05 tensor cores with P kept in tensor memory, head dim 64, 16-bit operands, fp32 softmax.
+// Flash attention on tcgen05 tensor cores with P kept in tensor memory: head dim 64, 16-bit operands, fp32 softmax.
 //   replaces xformers.ops.memory_efficient_attention (R/lvdm/modules/attention.py:177,189), the einsum softmax path
 //   (attention.py:105-129) and F.scaled_dot_product_attention with the boolean epipolar mask (R/model/modules/epipolar.py:99).
 //
-// Round-2 rebuild of attn_tc.cu's pipeline (profiles/r01h_ncu_full.txt: the round-1 kernel spent ~2050 cycles per 64-key tile
-// against ~256 cycles of MMA; its four softmax warps made two TMEM passes per tile - max + masked-score write-back, then exp - and
-// P went through shared memory with a proxy fence, so softmax(j+1) had to wait for PV(j)).  What changed:
-//   * ONE pass over S: the scores of a tile are read from TMEM once into registers, the mask is applied there (a packed 32-bit
-//     word per 32-key chunk and row; masked scores become -inf in registers, nothing is written back), then max, exp2, sum.
-//   * LAZY rescale (FA-4 style): the running reference maximum of a row is only raised when the tile maximum exceeds it by more
-//     than 2^8; probabilities are then at most 256 (exact in bf16 / fp16 and fp32 sums), and the O accumulator is touched by the
-//     softmax warps only in those rare tiles - the per-tile wait for PV(j-1) is gone from the common path.
-//   * P stays in TENSOR MEMORY: the 16-bit probabilities are stored with tcgen05.st over the first 32 columns of the S buffer
-//     they came from and PV is issued as tcgen05.mma with the A operand from TMEM (no shared-memory P tile, no
-//     fence.proxy.async).  S is double-buffered, so P is too: QK(j+2) overwrites buffer j&1 only after PV(j), which the in-order
-//     tensor pipe guarantees because both are issued by the same thread.
-//   * packed-mask words are fetched one tile ahead.
-// One CTA = 128 query rows of one (batch, head); 64-key tiles (two image rows of a 32x32 latent frame) keep the epipolar tile map
-// fine-grained; two CTAs per SM (TMEM 2 x 64 S/P columns + 64 O columns = 192 -> 256 allocated).
+// Round-2 rebuild of the round-1 pipeline (profiles/r01h_ncu_full.txt: ~2050 cycles per 64-key tile against ~256 cycles of MMA; four
+// softmax warps made two TMEM passes per tile - max + masked-score write-back, then exp - P went through shared memory with a
+// proxy fence, and softmax(j+1) waited for PV(j)).  One CTA = 128 query rows of one (batch, head), 64-key tiles (two image rows of
+// a 32x32 latent frame keep the epipolar tile map fine-grained), two CTAs per SM.  Per tile:
+//     S = Q K^T          tcgen05.mma 128x64x16 (x4), operands K-major in 128B-swizzled smem (TMA); S double-buffered in TMEM
+//     P_h = softmax      the two 32-key HALVES of a tile are two INDEPENDENT online-softmax streams, each with its own reference
+//                        maximum, row sum and O accumulator (split-K style): a stream never needs the other half's maximum, so each
+//                        half gets its own warp - 8 softmax warps per CTA, 4 per SM sub-partition with two CTAs per SM, which is what
+//                        keeps the MUFU (exp2) pipe busy: with head dim 64 the kernel is exp2 / issue bound, not MMA bound
+//                        (8192 exp2 per tile = 512 cycles of the SM's 16-lane MUFU against 256 cycles of MMA).
+//                        One pass: scores are read from TMEM once, the mask is applied in registers (a packed 32-bit word per row and
+//                        32-key chunk; masked scores become -inf, nothing is written back), then max, exp2, sum.
+//                        LAZY rescale (FA-4 style): the reference maximum of a stream is raised only when a tile exceeds it by more
+//                        than 2^8 (probabilities are then <= 256: exact in bf16 / fp16 and in the fp32 sums), so the O accumulator is
+//                        touched by the softmax warps only in those rare tiles and nothing waits for PV(j-1) on the common path.
+//                        P stays in TENSOR MEMORY: the 16-bit probabilities are stored (tcgen05.st) over the first 16 of the 32 S
+//                        columns they came from - no shared-memory P tile, no fence.proxy.async.
+//     O_h += P_h V_h     tcgen05.mma with the A operand FROM TMEM (128x64x16, x2 per half), V as MN-major operand straight from its
+//                        [key, d] layout.  QK(j+2) overwrites S buffer j&1 (= P(j)) only after PV(j): the tensor pipe executes one
+//                        thread's MMAs in issue order.
+// Epilogue: out = (a_0 O_0 + a_1 O_1) / (a_0 l_0 + a_1 l_1), a_h = 2^(m_h - max(m_0, m_1)); the (m, l) pairs of a row are exchanged
+// once through shared memory, each thread of the pair writes half of the head dim.
+// TMEM: 2 x 64 S/P columns + 2 x 64 O columns = 256.  Packed-mask words are fetched one tile ahead.
 //
 // Mask forms (all produce the same 32-bit word per (row, 32-key chunk), so outputs are bit-identical across forms):
 //   MODE 0  dense / ragged tails / register-token segment, and the per-sample packed epipolar mask (c2v_epipolar_bitmask)
 //   MODE 1  materialised byte mask in the reference's format, and the exact epipolar predicate on arbitrary grids (rolled loop)
 //   MODE 2  the exact epipolar predicate on square power-of-two grids, evaluated in-kernel from the 3x3 fundamental matrices with
 //           the reference's fp32 operation order (R/model/camcontexti2v.py:229-239)
-#include "attn_tc.h"
+#include "attn.h"
 #include "common.cuh"
 
 namespace c2v {
@@ -40,10 +48,6 @@ constexpr int FA_D = 64;
 // 1: one elected lane per softmax warp arrives on p_full (count 4) after __syncwarp; 0: every thread arrives (count 128)
 #ifndef C2V_FA_WARP_ARRIVE
 #define C2V_FA_WARP_ARRIVE 1
-#endif
-// of every 8 probabilities, this many are computed by a polynomial 2^x on the FMA pipe instead of MUFU.EX2 (0 = all on MUFU)
-#ifndef C2V_FA_POLY
-#define C2V_FA_POLY 0
 #endif
 // debug builds only (-DC2V_FA_TIMING=1): warp 2 of a few CTAs prints its per-phase cycle totals (clock64) at the end
 #ifndef C2V_FA_TIMING
@@ -105,7 +109,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 struct FaLine {
     float l0, l1, l2;
 };
-// Normalised epipolar line of query pixel (xi, yi) in frame t2 (camcontexti2v.py:229-236); same arithmetic as attn_tc.cu / epipolar.cu
+// Normalised epipolar line of query pixel (xi, yi) in frame t2 (camcontexti2v.py:229-236); same arithmetic as epi_maps.cu / epipolar.cu
 __device__ __forceinline__ FaLine fa_epi_line(const float* __restrict__ f, float xi, float yi) {
     float a0 = __fmaf_rn(f[2], 1.0f, __fmaf_rn(f[1], yi, __fmul_rn(f[0], xi)));
     float a1 = __fmaf_rn(f[5], 1.0f, __fmaf_rn(f[4], yi, __fmul_rn(f[3], xi)));
@@ -131,20 +135,6 @@ __device__ __forceinline__ float fa_max32(const uint32_t (&v)[32]) {
     return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
 }
 
-// 2^x for x <= 8 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-4 minimax polynomial of
-// 2^f (max rel. error 4e-6, far below the 2^-11 / 2^-8 rounding of the 16-bit P operand), exponent inserted by an integer add.
-// x is clamped at -126 so that the exponent field cannot wrap; callers zero masked (-inf) entries themselves.
-__device__ __forceinline__ float fa_exp2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = __fadd_rn(x, 12582912.0f);                 // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
-    const float f = __fadd_rn(x, -__fadd_rn(t, -12582912.0f));
-    float p = __fmaf_rn(9.6181291076e-3f, f, 5.5504108665e-2f);
-    p = __fmaf_rn(p, f, 2.4022650696e-1f);
-    p = __fmaf_rn(p, f, 6.9314718056e-1f);
-    p = __fmaf_rn(p, f, 1.0f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 template <int LOGW, int D, int MODE>
 __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(const __grid_constant__ AttnKernelArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -160,15 +150,7 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
     int* n_act_s = reinterpret_cast<int*>(bars + 19);
 
     const int warp = threadIdx.x >> 5;
-    // CTA -> (query tile, head); with an epipolar tile map the CTAs are issued heaviest query tile first (see attn_tc.cu)
     const int b = blockIdx.z;
-    int q_tile = blockIdx.x, head = blockIdx.y;
-    if (p.tile_map) {
-        const int lin = blockIdx.x + gridDim.x * blockIdx.y;
-        head = lin % gridDim.y;
-        q_tile = (int)p.tile_map[((size_t)b * gridDim.x + lin / gridDim.y) * p.tile_map_words + (p.tile_map_words - 1)];
-    }
-    const int q0 = q_tile * FA_BM;
     const int bkv = b / p.kv_div;
     const int n_main = (p.lk + FA_BN - 1) / FA_BN;
     const int n_tiles = n_main + (p.lk2 > 0 ? 1 : 0);       // last tile = register-token segment
@@ -202,6 +184,17 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
         tmem_alloc(tmem_ptr, FA_TMEM_COLS);
         tmem_relinquish();
     }
+    pdl_entry();      // CTA-local set-up above overlaps the previous kernel's tail; global memory is touched only below
+    // CTA -> (query tile, head).  With an epipolar tile map the CTAs are issued heaviest query tile first (longest-processing-time
+    // order, all heads of a tile back to back): the work per query tile varies 2-3x with the number of key tiles visited and the
+    // grid is only ~2 waves deep, so in-order dispatch would otherwise leave a long tail.
+    int q_tile = blockIdx.x, head = blockIdx.y;
+    if (p.tile_map) {
+        const int lin = blockIdx.x + gridDim.x * blockIdx.y;
+        head = lin % gridDim.y;
+        q_tile = (int)p.tile_map[((size_t)b * gridDim.x + lin / gridDim.y) * p.tile_map_words + (p.tile_map_words - 1)];
+    }
+    const int q0 = q_tile * FA_BM;
     // key tiles this query tile visits (epipolar tile map: tiles that cannot contain an unmasked pair are never loaded)
     uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + FA_OFF_LIST);
     if (warp == 2) {
@@ -468,12 +461,10 @@ __global__ void __launch_bounds__(FA_THREADS, C2V_FA_MIN_CTAS) attn_fa_kernel(co
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float2 x = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
-                float2 e;
-                constexpr int NP = C2V_FA_POLY;                   // elements per 8 on the FMA pipe
-                const int pos = (2 * i) & 7;                      // position of the pair's first element in its group of 8
-                const bool px = pos < NP, py = pos + 1 < NP;
-                e.x = px ? (v[2 * i] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.x)) : fast_exp2(x.x);
-                e.y = py ? (v[2 * i + 1] == FA_NEG_INF ? 0.f : fa_exp2_poly(x.y)) : fast_exp2(x.y);
+                // exp2 on the MUFU pipe.  (A Cody-Waite / degree-4 polynomial 2^x on the FMA pipe for 1 or 2 of every 8 elements, FA-4
+                // style, measured SLOWER here - 55 -> 61 / 68 us dense, 268 -> 307 / 344 us epipolar: with head dim 64 the softmax warps
+                // are issue-bound as much as MUFU-bound - and was removed.)
+                const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
                 if (i & 1) lb = fadd2(lb, e);
                 else la = fadd2(la, e);
                 w[i] = pack_bf16(e.x, e.y);
@@ -607,8 +598,7 @@ static int launch_fa(const AttnKernelArgs& a, int q_tiles, int heads, int batch,
         C2V_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel<LOGW, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         attr_set = true;
     }
-    attn_fa_kernel<LOGW, D, MODE><<<dim3(q_tiles, heads, batch), FA_THREADS, FA_SMEM, st>>>(a);
-    C2V_CHECK_CUDA(cudaGetLastError());
+    C2V_CHECK_CUDA(launch(attn_fa_kernel<LOGW, D, MODE>, dim3(q_tiles, heads, batch), dim3(FA_THREADS), FA_SMEM, st, a));
     return OK;
 }
 

@@ -1,12 +1,12 @@
 // Dense attention with a SHORT key sequence (the API routes lk <= 128 here; the kernel handles up to 256), head dim 64: text
 // cross-attention (77 keys), per-frame image cross-attention (16 keys), spatial self-attention of the 8x8 / 4x4 levels (64 / 16).
-//   replaces the same reference calls as attn_tc.cu (R/lvdm/modules/attention.py:105-144, 177, 189) for these shapes.
+//   replaces the same reference calls as attn_fa.cu (R/lvdm/modules/attention.py:105-144, 177, 189) for these shapes.
 // A 128 x 64 tcgen05 tile pipeline is mostly fixed latency here (one or two key tiles per CTA: ~20 us per launch whatever the
 // size); with all of K and V resident in shared memory the problem is a warp-level one:
 //   one warp = 16 query rows; S = Q K^T by mma.sync m16n8k16 (fragments by ldmatrix), online softmax over 64-key blocks on the
 //   accumulator fragments (a row lives in one quad), O += P V with P re-used from the S accumulators and V by ldmatrix.trans.
 // 8 warps (128 queries) per CTA share the K / V rows of their (kv batch, head).  HBM-bound: q + out once, K / V from L2.
-#include "attn_tc.h"
+#include "attn.h"
 #include "common.cuh"
 
 namespace c2v {
@@ -44,6 +44,7 @@ struct AttnSmallArgs {
 };
 
 __global__ void __launch_bounds__(AS_WARPS * 32, 2) attn_small_kernel(const AttnSmallArgs p) {
+    pdl_entry();
     extern __shared__ __align__(16) uint8_t as_smem[];
     const int lk_pad = (p.lk + 15) & ~15;
     __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(as_smem);
@@ -208,7 +209,7 @@ int attn_small_launch(const void* q, const void* k, const void* v, void* out, in
                                             (int)(((size_t)2 * AS_MAX_LK + AS_WARPS * 16) * AS_LD * sizeof(__nv_bfloat16))));
         attr_set = true;
     }
-    attn_small_kernel<<<dim3((lq + AS_WARPS * 16 - 1) / (AS_WARPS * 16), heads, bq), AS_WARPS * 32, smem, st>>>(a);
+    C2V_CHECK_CUDA(launch(attn_small_kernel, dim3((lq + AS_WARPS * 16 - 1) / (AS_WARPS * 16), heads, bq), dim3(AS_WARPS * 32), smem, st, a));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -17,6 +17,7 @@ constexpr int TA_LD = 66;   // padded row stride in bf16 elements (33 words: con
 template <int T>
 __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                                       int B, int HW, int heads) {
+    pdl_entry();
     constexpr int G = 32 / T;          // lanes sharing one query row
     constexpr int KPL = T / G;         // keys per lane
     constexpr int DPL = 64 / G;        // output dims per lane
@@ -134,6 +135,7 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 
 __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal16_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                                             int B, int HW, int heads) {
+    pdl_entry();
     constexpr int T = 16;
     __shared__ __align__(16) __nv_bfloat16 sm[TA_WARPS][3][T][TM_LD];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,8 +222,8 @@ int attention_temporal_launch(const void* qkv, void* out, int B, int T, int HW, 
     const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     switch (T) {
-        case 8: attn_temporal_kernel<8><<<grid, TA_WARPS * 32, 0, st>>>(q, o, B, HW, heads); break;
-        case 16: attn_temporal16_mma_kernel<<<grid, TA_WARPS * 32, 0, st>>>(q, o, B, HW, heads); break;
+        case 8: C2V_CHECK_CUDA(launch(attn_temporal_kernel<8>, dim3(grid), dim3(TA_WARPS * 32), 0, st, q, o, B, HW, heads)); break;
+        case 16: C2V_CHECK_CUDA(launch(attn_temporal16_mma_kernel, dim3(grid), dim3(TA_WARPS * 32), 0, st, q, o, B, HW, heads)); break;
         default: return ERR_UNSUPPORTED;
     }
     C2V_CHECK_CUDA(cudaGetLastError());

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 // ------------------------------------------------------------------------------------------------
 // 16-bit operand type of every tensor-core GEMM / attention operand and of every bf16 activation buffer.
@@ -38,6 +40,44 @@ enum Status : int { OK = 0, ERR_BAD_ARG = 1, ERR_CUDA = 2, ERR_TMA_ENCODE = 3, E
         cudaError_t _e = (expr);                  \
         if (_e != cudaSuccess) return c2v::ERR_CUDA; \
     } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the step is launched with the programmatic-stream-serialization
+// attribute (c2v::launch below) and starts with pdl_entry(): `launch_dependents` lets the NEXT kernel of the stream / graph branch
+// be scheduled as soon as every CTA of this one is resident, so its prologue (barrier init, TMEM allocation, descriptor prefetch)
+// and its launch latency overlap this kernel's tail; `wait` then blocks until the PREVIOUS kernel has completed and its writes are
+// visible.  Rule: no global memory access (read or write) before pdl_entry().  C2V_PDL=0 in the environment turns the
+// attribute off (the two instructions are then no-ops) for A/B measurements.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_entry() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("C2V_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// kernel<<<grid, block, smem, st>>>(args...) with the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

@@ -17,6 +17,7 @@ static inline int grid_for(int64_t work, int threads, int cap = 148 * 16) {
 // ------------------------------------------------------------------------------------------------
 template <bool OUT_BF16>
 __global__ void to_cl_kernel(const float* __restrict__ in, void* __restrict__ out, int C, int S, int Cpad) {
+    pdl_entry();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -38,6 +39,7 @@ __global__ void to_cl_kernel(const float* __restrict__ in, void* __restrict__ ou
 }
 
 __global__ void from_cl_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int S) {
+    pdl_entry();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -55,9 +57,9 @@ int to_channels_last_launch(const float* in, void* out, int B, int C, int S, int
     if (Cpad < C || B <= 0 || B > 65535) return ERR_BAD_ARG;
     dim3 grid((S + 31) / 32, (Cpad + 31) / 32, B), block(32, 8);
     if (out_bf16)
-        to_cl_kernel<true><<<grid, block, 0, st>>>(in, out, C, S, Cpad);
+        C2V_CHECK_CUDA(launch(to_cl_kernel<true>, grid, block, 0, st, in, out, C, S, Cpad));
     else
-        to_cl_kernel<false><<<grid, block, 0, st>>>(in, out, C, S, Cpad);
+        C2V_CHECK_CUDA(launch(to_cl_kernel<false>, grid, block, 0, st, in, out, C, S, Cpad));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
@@ -65,7 +67,7 @@ int to_channels_last_launch(const float* in, void* out, int B, int C, int S, int
 int from_channels_last_launch(const float* in, float* out, int B, int C, int S, cudaStream_t st) {
     if (B <= 0 || B > 65535) return ERR_BAD_ARG;
     dim3 grid((S + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    from_cl_kernel<<<grid, block, 0, st>>>(in, out, C, S);
+    C2V_CHECK_CUDA(launch(from_cl_kernel, grid, block, 0, st, in, out, C, S));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
@@ -86,6 +88,7 @@ __device__ __forceinline__ float sat16(float x) {
 
 __global__ void concat_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ of, __nv_bfloat16* __restrict__ ob,
                               int64_t rows, int Ca, int Cb, float s16) {
+    pdl_entry();
     const int nv = (Ca + Cb) >> 2, nva = Ca >> 2;
     const int64_t total = rows * nv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -103,13 +106,14 @@ __global__ void concat_kernel(const float* __restrict__ a, const float* __restri
 int concat_channels_launch(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t rows, int Ca, int Cb, float scale16,
                            cudaStream_t st) {
     if (Ca % 4 || Cb % 4) return ERR_UNSUPPORTED;
-    concat_kernel<<<grid_for(rows * ((Ca + Cb) >> 2), 256), 256, 0, st>>>(a, b, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, Ca, Cb,
-                                                                          scale16);
+    C2V_CHECK_CUDA(launch(concat_kernel, dim3(grid_for(rows * ((Ca + Cb) >> 2), 256)), dim3(256), 0, st, a, b, out_f32,
+                          reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, Ca, Cb, scale16));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n4, int64_t n, float s) {
+    pdl_entry();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = *reinterpret_cast<const float4*>(in + i * 4);
         *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16(sat16(v.x * s), sat16(v.y * s)), pack_bf16(sat16(v.z * s), sat16(v.w * s)));
@@ -119,13 +123,14 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 }
 
 int cast_bf16_launch(const float* in, void* out, int64_t n, float scale, cudaStream_t st) {
-    cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n / 4, n, scale);
+    C2V_CHECK_CUDA(launch(cast_bf16_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, st, in, reinterpret_cast<__nv_bfloat16*>(out), n / 4, n, scale));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
 
 // nearest 2x upsample feeding the Upsample conv (openaimodel3d.py:101-105)
 __global__ void upsample2x_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+    pdl_entry();
     const int nv = C >> 2;
     const int64_t total = (int64_t)N * 4 * H * W * nv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -141,7 +146,7 @@ __global__ void upsample2x_kernel(const float* __restrict__ in, __nv_bfloat16* _
 
 int upsample2x_launch(const float* in, void* out, int N, int H, int W, int C, cudaStream_t st) {
     if (C % 4) return ERR_UNSUPPORTED;
-    upsample2x_kernel<<<grid_for((int64_t)N * 4 * H * W * (C >> 2), 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), N, H, W, C);
+    C2V_CHECK_CUDA(launch(upsample2x_kernel, dim3(grid_for((int64_t)N * 4 * H * W * (C >> 2), 256)), dim3(256), 0, st, in, reinterpret_cast<__nv_bfloat16*>(out), N, H, W, C));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
@@ -150,6 +155,7 @@ int upsample2x_launch(const float* in, void* out, int N, int H, int W, int C, cu
 // pad_lo = 1: symmetric padding 1 (UNet Downsample, openaimodel3d.py:68-70); pad_lo = 0: zero padding on the right / bottom only
 // (VAE encoder Downsample, ae_modules.py:102-106)
 __global__ void im2col_s2_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C, int pad_lo) {
+    pdl_entry();
     const int nv = C >> 2, Ho = H >> 1, Wo = W >> 1;
     const int64_t total = (int64_t)N * Ho * Wo * 9 * nv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -168,7 +174,7 @@ __global__ void im2col_s2_kernel(const float* __restrict__ in, __nv_bfloat16* __
 
 int im2col_s2_launch(const float* in, void* out, int N, int H, int W, int C, int pad_lo, cudaStream_t st) {
     if (C % 4 || H % 2 || W % 2) return ERR_UNSUPPORTED;
-    im2col_s2_kernel<<<grid_for((int64_t)N * (H / 2) * (W / 2) * 9 * (C >> 2), 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), N, H, W, C, pad_lo);
+    C2V_CHECK_CUDA(launch(im2col_s2_kernel, dim3(grid_for((int64_t)N * (H / 2) * (W / 2) * 9 * (C >> 2), 256)), dim3(256), 0, st, in, reinterpret_cast<__nv_bfloat16*>(out), N, H, W, C, pad_lo));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
@@ -199,6 +205,7 @@ constexpr int SK_SMEM_FLOATS = 12288;   // 48 KB of staged activations per CTA
 __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ out, int M, int N, int K,
                                                             int silu_in, int mb) {
+    pdl_entry();
     extern __shared__ float xs[];           // [mb][K]
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -262,14 +269,15 @@ int skinny_linear_launch(const float* in, const void* w, const float* bias, floa
     int mb = SK_SMEM_FLOATS / K;
     if (mb > SK_MAXM) mb = SK_MAXM;
     if (mb > M) mb = M;
-    skinny_linear_kernel<<<(N + 7) / 8, 256, (size_t)mb * K * sizeof(float), st>>>(in, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N,
-                                                                                  K, silu_in, mb);
+    C2V_CHECK_CUDA(launch(skinny_linear_kernel, dim3((N + 7) / 8), dim3(256), (size_t)mb * K * sizeof(float), st, in,
+                          reinterpret_cast<const __nv_bfloat16*>(w), bias, out, M, N, K, silu_in, mb));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
 
 // sinusoidal embedding (utils_diffusion.py:8-28): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / half)
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int n, int dim) {
+    pdl_entry();
     const int half = dim >> 1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * half; i += gridDim.x * blockDim.x) {
         const int r = i / half, c = i - r * half;
@@ -282,7 +290,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* 
 
 int timestep_embedding_launch(const int64_t* t, float* out, int n, int dim, cudaStream_t st) {
     if (dim % 2) return ERR_UNSUPPORTED;
-    timestep_embedding_kernel<<<grid_for((int64_t)n * (dim / 2), 128, 64), 128, 0, st>>>(t, out, n, dim);
+    C2V_CHECK_CUDA(launch(timestep_embedding_kernel, dim3(grid_for((int64_t)n * (dim / 2), 128, 64)), dim3(128), 0, st, t, out, n, dim));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
@@ -318,6 +326,7 @@ __global__ void __launch_bounds__(1024) cfg_ddim_kernel(const float* __restrict_
                                                         const float* __restrict__ enc, const float* __restrict__ noise, float* __restrict__ x_prev,
                                                         float* __restrict__ pred_x0, int64_t n, float scale, float cam_w, float phi, float a_t,
                                                         float a_prev, float sigma_t, float sqrt_one_minus_at) {
+    pdl_entry();
     __shared__ double sh[32];
     const size_t base = (size_t)blockIdx.x * n;
     x += base; ec += base; eu += base; noise += base; x_prev += base; pred_x0 += base;
@@ -359,7 +368,7 @@ int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, con
                            float* pred_x0, int B, int64_t n, float scale, float cam_w, float phi, float a_t, float a_prev, float sigma_t,
                            float sqrt_one_minus_at, cudaStream_t st) {
     if (B <= 0 || n <= 1) return ERR_BAD_ARG;
-    cfg_ddim_kernel<<<B, 1024, 0, st>>>(x, ec, eu, enc, noise, x_prev, pred_x0, n, scale, cam_w, phi, a_t, a_prev, sigma_t, sqrt_one_minus_at);
+    C2V_CHECK_CUDA(launch(cfg_ddim_kernel, dim3(B), dim3(1024), 0, st, x, ec, eu, enc, noise, x_prev, pred_x0, n, scale, cam_w, phi, a_t, a_prev, sigma_t, sqrt_one_minus_at));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

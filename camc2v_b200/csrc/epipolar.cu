@@ -1,7 +1,7 @@
 // Camera-geometry kernels.
 //   epipolar mask   CamContextI2V.get_epipolar_mask, R/model/camcontexti2v.py:202-271 (bit-exact, boolean)
 //   Pluecker / ray  CameraControlLVDM.ray_condition, R/model/base.py:112-174
-// The hot path never materialises the mask (attn_tc.cu evaluates it in-tile); this kernel exists for the
+// The hot path never materialises the mask (attn_fa.cu reads the packed per-sample mask or evaluates the predicate in-tile); this kernel exists for the
 // reference-facing API (`sample_locs_dict`) and for the bit-exactness tests.  It writes one byte per pair:
 // pure HBM-write bound (268 MB per sample at 32x32x16), 16 mask bytes per thread, 512 B per warp store.
 #include "common.cuh"

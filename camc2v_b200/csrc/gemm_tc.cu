@@ -18,13 +18,6 @@
 #include "common.cuh"
 #include "gemm_tc.h"
 
-// 1: the epilogue warps prefetch the bias / row-bias lines of their tile into L1 while they wait for the accumulator.  The ncu
-// captures of the 32x32-level GEMMs put 6-10 % of their stall samples on the first bias add of the epilogue (long scoreboard).
-// Written when the round's GPU time was spent; off until measured (when off the instruction stream is the one of the measured build, up to two renamed uniform registers).
-#ifndef C2V_GEMM_BIAS_PREFETCH
-#define C2V_GEMM_BIAS_PREFETCH 0
-#endif
-
 namespace c2v {
 
 constexpr int BM = 128;
@@ -87,6 +80,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 2) gemm_tc_kernel(const _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_entry();      // everything above is CTA-local set-up and overlaps the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -174,37 +168,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 2) gemm_tc_kernel(const _
         const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
         const float* rb = (!part && p.rowbias && row_ok) ? p.rowbias + (size_t)(m / p.rows_per_group) * p.N : nullptr;
         const float* bias = part ? nullptr : p.bias;
-#if C2V_GEMM_BIAS_PREFETCH
-        // While the main loop runs the epilogue warps only wait: pull the tile's bias / row-bias lines into L1 now, so that the
-        // first `f[j] += bias[n]` after the accumulator barrier is an L1 hit instead of a ~600-cycle L2 round trip.  In-bounds
-        // addresses only (the last N tile may be ragged).
-        {
-            const int col = n0 + (int)lane_id() * 32;            // one 128-byte line per lane
-            if (col < p.N && (int)lane_id() * 32 < BN) {
-                if (bias) asm volatile("prefetch.global.L1 [%0];" ::"l"(bias + col));
-                if (rb) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + col));
-            }
-        }
-#endif
         if (EPI_WARPS > 4 && (warp >= 6) && p.epi != EPI_GEGLU) {
             // the second epilogue group only exists for the GEGLU epilogue
-        } else if (part && p.cluster_reduce) {
-            // ---- split-K inside a thread-block cluster: park the raw fp32 partial tile in (now idle) pipeline smem, in the
-            //      same conflict-free chunk-major swizzled layout as the TMA staging; the reduction follows the cluster barrier
-            mbar_wait<200>(acc_bar, 0);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                if (n0 + c * 32 >= p.N) break;
-                uint32_t v[32];
-                tmem_ld32(trow + c * 32, v);
-                tmem_ld_wait();
-                uint8_t* rowp = smem + c * 16384 + r * 128;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    *reinterpret_cast<uint4*>(rowp + ((k ^ (r & 7)) << 4)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-            }
-            tc_fence_before();
         } else if (p.tma_epi) {
             // ---- TMA epilogue: residual tile fetched by TMA into the (now idle) pipeline stages with every 32-column chunk
             //      in flight at once; results staged in shared memory (hardware swizzle, conflict-free) and written back by
@@ -420,51 +385,6 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 2) gemm_tc_kernel(const _
         tc_fence_before();
         }
     }
-    if (p.splits > 1 && p.cluster_reduce) {
-        // Deterministic split-K reduction through distributed shared memory: CTA z of the cluster owns a slice of the tile's
-        // rows, sums the S partials in fixed order z' = 0..S-1 (ld.shared::cluster), applies bias / row bias / residual and
-        // writes the final rows.  No workspace in HBM, no second kernel.
-        cluster_sync_all();
-        if (warp >= 2) {
-            const int S_ = p.splits, z = blockIdx.z;
-            const int e = threadIdx.x - 64;
-            const int rows_per = (p.tile_rows + S_ - 1) / S_;
-            const int r_begin = z * rows_per, r_end = min(p.tile_rows, r_begin + rows_per);
-            const int ncol4 = min(BN, p.N - n0) >> 2;
-            const uint32_t sbase = smem_u32(smem);
-            const int m_base = m_tile * p.tile_rows;
-            for (int idx = e; idx < (r_end - r_begin) * ncol4; idx += 128) {
-                const int rr = r_begin + idx / ncol4, c4 = idx - (idx / ncol4) * ncol4;
-                const int col = c4 * 4, m = m_base + rr;
-                if (m >= p.M) continue;
-                const uint32_t off = (uint32_t)((col >> 5) * 16384 + rr * 128 + ((((col & 31) >> 2) ^ (rr & 7)) << 4));
-                float4 acc = ld_dsmem_f4(sbase + off, 0);
-                for (int zz = 1; zz < S_; ++zz) {
-                    const float4 t = ld_dsmem_f4(sbase + off, (uint32_t)zz);
-                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-                }
-                const int n = n0 + col;
-                if (p.bias) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n);
-                    acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
-                }
-                if (p.rowbias) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(p.rowbias + (size_t)(m / p.rows_per_group) * p.N + n);
-                    acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
-                }
-                if (p.residual) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + n);
-                    acc.x += r4.x; acc.y += r4.y; acc.z += r4.z; acc.w += r4.w;
-                }
-                if (p.out_bf16)
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n) =
-                        make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
-                else
-                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n) = acc;
-            }
-        }
-        cluster_sync_all();          // nobody leaves (and frees its shared memory) while a peer may still read it
-    }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -494,25 +414,7 @@ static int launch(const GemmKernelArgs& a, int m_tiles, int n_tiles, cudaStream_
     const int min_stages = a.epi == EPI_GEGLU ? 2 : MIN_STAGES;       // the GEGLU epilogue stores straight from registers
     if (stages < min_stages) stages = min_stages;
     b.stages = stages;
-    if (a.splits > 1 && a.cluster_reduce) {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(m_tiles, n_tiles, a.splits);
-        cfg.blockDim = dim3(THREADS);
-        cfg.dynamicSmemBytes = S::total(stages);
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 1;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = a.splits;          // the K splits of one output tile are one cluster
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        C2V_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI_WARPS>, b));
-        return OK;
-    }
-    gemm_tc_kernel<BN, EPI_WARPS><<<dim3(m_tiles, n_tiles, a.splits), THREADS, S::total(stages), st>>>(b);
-    C2V_CHECK_CUDA(cudaGetLastError());
+    C2V_CHECK_CUDA(launch(gemm_tc_kernel<BN, EPI_WARPS>, dim3(m_tiles, n_tiles, a.splits), dim3(THREADS), S::total(stages), st, b));
     return OK;
 }
 
@@ -521,6 +423,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             const float* __restrict__ rowbias, int rows_per_group,
                                                             const float* __restrict__ residual, int ldr, void* __restrict__ out, int ldo,
                                                             int out_bf16) {
+    pdl_entry();
     const int nv = N >> 2;
     const size_t plane = (size_t)M * N;
     const long long total = (long long)M * nv;
@@ -564,8 +467,8 @@ int splitk_reduce_launch(const float* ws, int splits, int M, int N, const float*
     long long work = (long long)M * (N >> 2);
     int grid = (int)((work + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
-    splitk_reduce_kernel<<<grid, 256, 0, st>>>(ws, splits, M, N, bias, rowbias, rows_per_group, residual, ldr, out, ldo, out_bf16);
-    C2V_CHECK_CUDA(cudaGetLastError());
+    C2V_CHECK_CUDA(launch(splitk_reduce_kernel, dim3(grid), dim3(256), 0, st, ws, splits, M, N, bias, rowbias, rows_per_group, residual, ldr, out, ldo,
+                          out_bf16));
     return OK;
 }
 

@@ -30,8 +30,7 @@ struct GemmKernelArgs {
     int ldo;
     int out_bf16;
     int stages;             // smem ring depth (set by gemm_tc_launch)
-    int splits;             // split-K factor (grid.z); > 1: raw fp32 partials go to `out` = ws[z][M][N] ...
-    int cluster_reduce;     // ... or (1) the splits of a tile form a thread-block cluster and reduce through distributed smem
+    int splits;             // split-K factor (grid.z); > 1: raw fp32 partials go to `out` = ws[z][M][N], reduced by splitk_reduce_kernel
 };
 
 int gemm_tc_launch(const GemmKernelArgs& a, int bn, int m_tiles, int n_tiles, cudaStream_t st);

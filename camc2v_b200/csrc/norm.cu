@@ -42,6 +42,7 @@ __device__ __forceinline__ GnMap gn_map(int C) {
 // partial (sum, sumsq) per (sample, slab, group)
 __global__ void __launch_bounds__(GN_THREADS, 2) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws, int rows, int C,
                                                               int rows_per_slab) {
+    pdl_entry();
     // Per-thread fp32 partials are combined across the CTA as 64-bit fixed point: integer atomics are
     // order-independent, so the statistics (and everything downstream) are bit-reproducible run to run.
     __shared__ long long s_sum[32], s_sq[32];
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_apply_kernel(const float* __
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               __nv_bfloat16* __restrict__ out, int rows, int C, int rows_per_slab,
                                                               float eps, int silu) {
+    pdl_entry();
     __shared__ float s_mean[32], s_rstd[32];
     __shared__ double s_ps[16][32], s_pq[16][32];
     const int n = blockIdx.y, slab = blockIdx.x, nslab = gridDim.x;
@@ -207,8 +209,9 @@ int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta,
     if (ns > 65535) return ERR_UNSUPPORTED;
     int rps;
     const int slabs = gn_slabs(ns, rows, C, &rps);
-    gn_stats_kernel<<<dim3(slabs, ns), GN_THREADS, 0, st>>>(x, ws, rows, C, rps);
-    gn_apply_kernel<<<dim3(slabs, ns), GN_THREADS, 0, st>>>(x, ws, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), rows, C, rps, eps, silu);
+    C2V_CHECK_CUDA(launch(gn_stats_kernel, dim3(slabs, ns), dim3(GN_THREADS), 0, st, x, ws, rows, C, rps));
+    C2V_CHECK_CUDA(launch(gn_apply_kernel, dim3(slabs, ns), dim3(GN_THREADS), 0, st, x, (const float*)ws, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out),
+                          rows, C, rps, eps, silu));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ add, __nv_bfloat16* __restrict__ out2,
                                                         float* __restrict__ out_f32, int rows, int C, float eps) {
+    pdl_entry();
     const int wpb = blockDim.x >> 5, stride = gridDim.x * wpb;
     int row = blockIdx.x * wpb + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -298,11 +302,11 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(out2);
     if (nv <= 3)
-        layernorm_kernel<3><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, o, add, o2, out_f32, rows, C, eps);
+        C2V_CHECK_CUDA(launch(layernorm_kernel<3>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps));
     else if (nv <= 5)
-        layernorm_kernel<5><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, o, add, o2, out_f32, rows, C, eps);
+        C2V_CHECK_CUDA(launch(layernorm_kernel<5>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps));
     else
-        layernorm_kernel<LN_MAXV><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, o, add, o2, out_f32, rows, C, eps);
+        C2V_CHECK_CUDA(launch(layernorm_kernel<LN_MAXV>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -33,9 +33,8 @@ def _chk(t: torch.Tensor, dtype, name: str):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM family
-# Split-K partials: through an HBM workspace + a reduce kernel (default: measured 10-20 % faster on B200 for this model's
-# shapes) or, with C2V_SPLITK_CLUSTER=1, through distributed shared memory of a thread-block cluster (no workspace).
-SPLITK_WORKSPACE = os.environ.get("C2V_SPLITK_CLUSTER", "0") != "1"
+# Split-K partials go through an fp32 workspace (L2-resident at these sizes) + a deterministic reduce kernel.  (A variant that
+# reduced inside a thread-block cluster through distributed shared memory measured 10-20 % slower in round 1 and was removed.)
 
 
 def tile_n(N: int, epi: int = EPI_LINEAR) -> int:
@@ -60,11 +59,9 @@ def _gemm(a, w, M, N, Cin, taps, a_mode, nb, d1, d2, lda, bias, rowbias, rows_pe
     sk = _lib.load().c2v_gemm_splitk(M, N, Cin, taps, epi)
     if sk > 1:
         d.splitk = sk
-        if SPLITK_WORKSPACE:        # partial tiles through an HBM workspace (L2-resident) + the deterministic reduce kernel
-            ws = torch.empty((sk, M, N), device=a.device, dtype=F32)
-            d.ws = _p(ws)
-            _lib.LAUNCHES += 1
-        # else ws = NULL: the K splits of a tile form a thread-block cluster and reduce through distributed smem
+        ws = torch.empty((sk, M, N), device=a.device, dtype=F32)     # partial tiles; reduced by the second kernel of the call
+        d.ws = _p(ws)
+        _lib.LAUNCHES += 1
     _lib.call("c2v_gemm", C.byref(d), _stream())
     return out
 

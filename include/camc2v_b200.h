@@ -62,11 +62,8 @@ typedef struct c2v_gemm_desc {
                               (see camc2v_b200.ops.geglu_interleave); out is bf16 [M, N/2] */
     int splitk;            /* 0/1: none.  > 1: split the K loop over `splitk` CTAs per tile (deep-K, few-tile GEMMs at the 16x16 /
                               8x8 / 4x4 levels); the partials are reduced deterministically (fixed order) with the fused epilogue */
-    float* ws;             /* non-NULL: fp32 scratch of splitk*M*N floats; partial tiles go through it (L2-resident at these
-                              sizes) and a second kernel reduces them.  This is what camc2v_b200.ops uses: measured 10-20 %
-                              faster on B200 for the UNet's shapes than the cluster variant.
-                              NULL (splitk <= 8): the `splitk` CTAs of a tile form one thread-block cluster and reduce through
-                              distributed shared memory - no workspace, one kernel, bit-identical result. */
+    float* ws;             /* required when splitk > 1: fp32 scratch of splitk*M*N floats; partial tiles go through it (L2-resident
+                              at these sizes) and a second kernel reduces them in fixed order. */
 } c2v_gemm_desc;
 
 int c2v_gemm(const c2v_gemm_desc* d, void* stream);

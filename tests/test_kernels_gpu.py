@@ -61,10 +61,10 @@ def test_linear(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,bf16", [(256, 1280, 5120, False), (1024, 1280, 5120, True), (2048, 640, 2560, False), (200, 1280, 3840, False)])
-def test_splitk_cluster_reduce_matches_workspace_path(M, N, K, bf16):
-    """Split-K through a thread-block cluster (partials reduced in distributed shared memory, ws = NULL) against the
-    workspace + reduce-kernel path (the default): same fixed summation order over the splits -> identical bits; and
-    run-to-run identical."""
+def test_splitk_is_deterministic_and_needs_a_workspace(M, N, K, bf16):
+    """Split-K (partials through the fp32 workspace, fixed summation order in the reduce kernel): correct, run-to-run identical;
+    the C entry point rejects a split-K call without a workspace."""
+    import ctypes as C
     ops = _ops()
     assert ops._lib.load().c2v_gemm_splitk(M, N, K, 1, 0) > 1
     a = rnd(M, K, seed=1, dtype=_dt())
@@ -72,16 +72,14 @@ def test_splitk_cluster_reduce_matches_workspace_path(M, N, K, bf16):
     bias, res, rb = rnd(N, seed=3), rnd(M, N, seed=4), rnd((M + 127) // 128, N, seed=5)
     odt = _dt() if bf16 else torch.float32
     ref = a.float() @ w.float().t() + bias + res + rb.repeat_interleave(128, dim=0)[:M]
-    outs = []
-    for legacy in (False, True, False):
-        ops.SPLITK_WORKSPACE = legacy
-        try:
-            outs.append(ops.linear(a, w, bias=bias, residual=res, rowbias=rb, rows_per_group=128, out_dtype=odt))
-        finally:
-            ops.SPLITK_WORKSPACE = True
-    close(outs[0], ref, 1e-2 if bf16 else 2e-3, "cluster split-K")
-    assert torch.equal(outs[0], outs[2]), "cluster split-K must be deterministic"
-    assert torch.equal(outs[0], outs[1]), "cluster reduce and workspace reduce must sum in the same order"
+    outs = [ops.linear(a, w, bias=bias, residual=res, rowbias=rb, rows_per_group=128, out_dtype=odt) for _ in range(2)]
+    close(outs[0], ref, 1e-2 if bf16 else 2e-3, "split-K")
+    assert torch.equal(outs[0], outs[1]), "split-K must be deterministic"
+    d = ops.GemmDesc()
+    out = torch.empty(M, N, device=DEV)
+    d.a, d.w, d.out = a.data_ptr(), w.data_ptr(), out.data_ptr()
+    d.M, d.N, d.Cin, d.taps, d.lda, d.ldo, d.splitk = M, N, K, 1, K, N, 2
+    assert ops._lib.load().c2v_gemm(C.byref(d), None) == 1          # ERR_BAD_ARG: no workspace
 
 
 def test_linear_strided_a_and_rowbias():

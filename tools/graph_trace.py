@@ -128,7 +128,7 @@ def by_shape(model, sampler, cond, uc, static, recs):
         elif name == "c2v_attention":
             d = a[0]._obj
             key = f"attn bq={d.bq} lq={d.lq} lk={d.lk}+{d.lk2} h={d.heads} kvdiv={d.kv_div} epi={int(bool(d.epi_F))}/{d.epi_d} acc={d.accumulate}"
-            log.append(("attn_tc", key, 4.0 * d.bq * d.lq * (d.lk + d.lk2) * d.heads * 64))
+            log.append(("attn_", key, 4.0 * d.bq * d.lq * (d.lk + d.lk2) * d.heads * 64))
         elif name == "c2v_groupnorm_silu":
             key = f"ns={a[5]} rows={a[6]} C={a[7]}"
             log.append(("gn_stats", "gn_stats " + key, 0.0))
@@ -156,7 +156,7 @@ def by_shape(model, sampler, cond, uc, static, recs):
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
     bad = 0
     for (frag, key, fl), r in zip(log, ks):
-        if frag not in r[3] and not (frag == "attn_tc" and "attn_tc" in r[3]):
+        if frag not in r[3]:
             bad += 1
         agg[key][0] += 1
         agg[key][1] += r[1] - r[0]
