@@ -340,37 +340,55 @@ class ResBlock(_Prepared, TimestepBlock):
 # derived-state caches: eviction that can never pull a buffer from under a captured CUDA graph
 # =================================================================================================
 _PINNED: Dict[int, int] = {}            # id(cache entry list) -> pin count; a pinned entry is never evicted
+_RECORD: Optional[dict] = None          # id -> entry: every cache entry touched since begin_cache_record() (also never evicted)
+CACHE_INSERTS = 0                       # number of cache entries created so far (the sampler checks that a capture creates none)
+
+
+def _touch(ent: list) -> list:
+    if _RECORD is not None:
+        _RECORD[id(ent)] = ent
+    return ent
+
+
+def _inserted(ent: list) -> list:
+    global CACHE_INSERTS
+    CACHE_INSERTS += 1
+    return _touch(ent)
 
 
 def _evict(cache: dict, limit: int) -> None:
-    """Drop the oldest unpinned entries once `cache` holds more than `limit`.  (The previous wholesale `.clear()` could free
-    tile maps / packed masks / projected K/V that a captured graph still points at; replays then read recycled memory.)"""
+    """Drop the oldest entries once `cache` holds more than `limit`, except entries pinned by a captured CUDA graph and entries
+    touched by the warm-up / capture in progress.  (The round-1 wholesale `.clear()` could free tile maps / packed masks /
+    projected K/V that a captured graph still points at; replays then read recycled memory.)"""
     if len(cache) <= limit:
         return
     for k in list(cache.keys()):
         if len(cache) <= limit:
             break
-        if id(cache[k]) not in _PINNED:
+        e = cache[k]
+        if id(e) not in _PINNED and not (_RECORD is not None and id(e) in _RECORD):
             del cache[k]
 
 
-def _all_cache_entries(model: Optional[nn.Module]):
-    for cache in (_CONTEXT_CACHE, _TILEMAP_CACHE, _BITMASK_CACHE, _PLUKER_CACHE):
-        yield from cache.values()
-    if model is not None:
-        for m in model.modules():
-            c = m.__dict__.get("_ctx_cache")
-            if c:
-                yield from c.values()
+def begin_cache_record() -> None:
+    """Start recording the cache entries a sequence of passes touches (the sampler brackets warm-up + capture with this)."""
+    global _RECORD
+    _RECORD = {}
 
 
-def pin_caches(model: Optional[nn.Module] = None) -> list:
-    """Called by the sampler right after a CUDA-graph capture: every cache entry alive now may be referenced by pointer from
-    the captured kernels, so it is pinned (kept, and still refreshed in place) until `unpin_caches(token)`."""
-    token = list(_all_cache_entries(model))          # holding the entry lists also keeps their buffers alive
-    for e in token:
+def end_cache_record() -> list:
+    global _RECORD
+    ents = list(_RECORD.values()) if _RECORD is not None else []
+    _RECORD = None
+    return ents
+
+
+def pin_entries(ents: list) -> list:
+    """Pin exactly the cache entries a captured graph uses: they are kept (and still refreshed in place) until
+    `unpin_caches(token)`.  The token holds the entries, so their buffers stay alive as long as the graph does."""
+    for e in ents:
         _PINNED[id(e)] = _PINNED.get(id(e), 0) + 1
-    return token
+    return list(ents)
 
 
 def unpin_caches(token: Optional[list]) -> None:
@@ -483,11 +501,11 @@ class CrossAttention(_Prepared):
         ent = cache.get(key)
         if ent is None:
             _evict(cache, 8)
-            ent = cache[key] = [ctx.gen, ops.linear(src, w, out_dtype=BF16), ctx, w, slot]
+            ent = cache[key] = _inserted([ctx.gen, ops.linear(src, w, out_dtype=BF16), ctx, w, slot])
         elif ent[0] != ctx.gen:
             ent[0] = ctx.gen
             ops.linear(src, w, out=ent[1])
-        return ent[1]
+        return _touch(ent)[1]
 
     def cross(self, n: torch.Tensor, ctx: ContextPack, bq: int, lq: int, residual, out_dtype=F32):
         p = self.pk()
@@ -535,13 +553,13 @@ def make_context_pack(context: torch.Tensor, T: int, text_len: int = 77, per_fra
     key = (context.data_ptr(), tuple(context.shape), T, text_len, per_frame, str(context.device))
     ent = _CONTEXT_CACHE.get(key)
     if ent is not None and ent[0] == context._version:
-        return ent[1]
+        return _touch(ent)[1]
     pack = _make_context_pack(context, T, text_len, per_frame, ent[1] if ent is not None else None)
     if ent is not None:                                  # same buffer refilled in place: keep the (possibly pinned) entry object
         ent[0], ent[1] = context._version, pack
-        return pack
+        return _touch(ent)[1]
     _evict(_CONTEXT_CACHE, 16)
-    _CONTEXT_CACHE[key] = [context._version, pack, context]
+    _CONTEXT_CACHE[key] = _inserted([context._version, pack, context])
     return pack
 
 
@@ -856,12 +874,12 @@ def _tile_map(Fm: torch.Tensor, T: int, H: int, W: int, d: int):
     ent = _TILEMAP_CACHE.get(key)
     if ent is None:
         _evict(_TILEMAP_CACHE, 64)
-        ent = _TILEMAP_CACHE[key] = [Fm._version, ops.epipolar_tile_map(Fm, T, H, W, d), Fm]
+        ent = _TILEMAP_CACHE[key] = _inserted([Fm._version, ops.epipolar_tile_map(Fm, T, H, W, d), Fm])
     elif ent[0] != Fm._version:
         ent[0] = Fm._version
         if ent[1] is not None:
             ops.epipolar_tile_map(Fm, T, H, W, d, out=ent[1])
-    return ent[1]
+    return _touch(ent)[1]
 
 
 def _bitmask(Fm: torch.Tensor, T: int, H: int, W: int, d: int):
@@ -871,12 +889,12 @@ def _bitmask(Fm: torch.Tensor, T: int, H: int, W: int, d: int):
     ent = _BITMASK_CACHE.get(key)
     if ent is None:
         _evict(_BITMASK_CACHE, 64)
-        ent = _BITMASK_CACHE[key] = [Fm._version, ops.epipolar_bitmask(Fm, T, H, W, d), Fm]
+        ent = _BITMASK_CACHE[key] = _inserted([Fm._version, ops.epipolar_bitmask(Fm, T, H, W, d), Fm])
     elif ent[0] != Fm._version:
         ent[0] = Fm._version
         if ent[1] is not None:
             ops.epipolar_bitmask(Fm, T, H, W, d, out=ent[1])
-    return ent[1]
+    return _touch(ent)[1]
 
 
 def _pluker_cl(p: torch.Tensor) -> torch.Tensor:
@@ -886,11 +904,11 @@ def _pluker_cl(p: torch.Tensor) -> torch.Tensor:
     ent = _PLUKER_CACHE.get(key)
     if ent is None:
         _evict(_PLUKER_CACHE, 64)
-        ent = _PLUKER_CACHE[key] = [p._version, ops.to_channels_last(_f32(p), B, C, T * h * w), p]
+        ent = _PLUKER_CACHE[key] = _inserted([p._version, ops.to_channels_last(_f32(p), B, C, T * h * w), p])
     elif ent[0] != p._version:
         ent[0] = p._version
         ops.to_channels_last(_f32(p), B, C, T * h * w, out=ent[1])
-    return ent[1]
+    return _touch(ent)[1]
 
 
 def refresh_camera_caches() -> None:

@@ -19,6 +19,7 @@ from __future__ import annotations
 from typing import Optional
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -26,6 +27,9 @@ import torch.nn as nn
 
 from . import ops
 from .modules import UNetModel
+
+
+_DEBUG_GRAPH = os.environ.get("C2V_DEBUG_GRAPH", "0") == "1"
 
 
 def make_beta_schedule_linear(n_timestep=1000, linear_start=0.00085, linear_end=0.012) -> np.ndarray:
@@ -122,6 +126,12 @@ class DDIMSampler(object):
             modules.unpin_caches(self._graph.get("pin"))
         self._graph = None
 
+    def __del__(self):
+        try:
+            self.reset_graph()          # a dead sampler must not leave its cache entries pinned forever
+        except Exception:
+            pass
+
     # -------------------------------------------------------------------------------------------- schedule
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
         """ddim.py:24-57; all per-step coefficients are kept as host fp32 numpy arrays."""
@@ -194,41 +204,59 @@ class DDIMSampler(object):
         key = (_leaf_key(conds), _leaf_key(kwargs), tuple(x.shape), str(x.dtype))
         if g is None or g["key"] != key:
             self.reset_graph()
-            sx, st = x.clone(), t.clone()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):          # warm-up outside capture: builds weight packs, fills allocator pools
-                for c in conds:
-                    self.model.apply_model(sx, st, c, **kwargs)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                # The cond and uncond passes are independent: capture them as parallel branches of the graph so that
-                # the small grids of the 8x8 / 4x4 levels and every kernel's last partial wave overlap with the other pass.
-                main = torch.cuda.current_stream()
-                branches = []
-                if self.concurrent_passes:
-                    for _ in conds[1:]:               # fork BEFORE anything is captured on main: the branches have no
-                        br = torch.cuda.Stream()      # dependency on the first pass
-                        br.wait_stream(main)
-                        branches.append(br)
-                outs = [self.model.apply_model(sx, st, conds[0], **kwargs)]
-                for i, c in enumerate(conds[1:]):
-                    if self.concurrent_passes:
-                        with torch.cuda.stream(branches[i]):
-                            outs.append(self.model.apply_model(sx, st, c, **kwargs))
-                    else:
-                        outs.append(self.model.apply_model(sx, st, c, **kwargs))
-                for br in branches:
-                    main.wait_stream(br)
             from . import modules
+            sx, st = x.clone(), t.clone()
+            # Every per-sample cache entry the passes touch (context packs, projected K/V, tile maps, packed masks, channels-last
+            # Pluecker copies) is recorded from the warm-up on: recorded entries cannot be evicted, so the capture below only HITS
+            # entries the warm-up created outside the graph, and exactly these entries are pinned for the lifetime of the graph.
+            modules.begin_cache_record()
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):          # warm-up outside capture: builds weight packs, fills allocator pools
+                    for c in conds:
+                        self.model.apply_model(sx, st, c, **kwargs)
+                torch.cuda.current_stream().wait_stream(side)
+                inserts0 = modules.CACHE_INSERTS
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    # The cond and uncond passes are independent: capture them as parallel branches of the graph so that
+                    # the small grids of the 8x8 / 4x4 levels and every kernel's last partial wave overlap with the other pass.
+                    main = torch.cuda.current_stream()
+                    branches = []
+                    if self.concurrent_passes:
+                        for _ in conds[1:]:               # fork BEFORE anything is captured on main: the branches have no
+                            br = torch.cuda.Stream()      # dependency on the first pass
+                            br.wait_stream(main)
+                            branches.append(br)
+                    outs = [self.model.apply_model(sx, st, conds[0], **kwargs)]
+                    for i, c in enumerate(conds[1:]):
+                        if self.concurrent_passes:
+                            with torch.cuda.stream(branches[i]):
+                                outs.append(self.model.apply_model(sx, st, c, **kwargs))
+                        else:
+                            outs.append(self.model.apply_model(sx, st, c, **kwargs))
+                    for br in branches:
+                        main.wait_stream(br)
+            finally:
+                touched = modules.end_cache_record()
+            if modules.CACHE_INSERTS != inserts0:
+                # a derived buffer was produced INSIDE the capture: with parallel branches another branch may read it without a
+                # dependency edge - never replay such a graph
+                raise RuntimeError("camc2v_b200.sampler: a per-sample cache entry was created during CUDA-graph capture "
+                                   "(the warm-up pass should have created it); refusing to replay a graph with unordered producers")
             # `refs` keeps every conditioning tensor of the key alive; `pin` marks the cache-derived buffers the captured kernels
-            # point at (tile maps, packed masks, channels-last Pluecker copies, context packs, projected K/V) as non-evictable.
+            # point at as non-evictable.
             g = self._graph = dict(key=key, graph=graph, x=sx, t=st, outs=outs, ec=outs[0], eu=outs[-1], refs=(list(conds), dict(kwargs)),
-                                   pin=modules.pin_caches(self.model))
+                                   pin=modules.pin_entries(touched))
         g["x"].copy_(x)
         g["t"].copy_(t)
         g["graph"].replay()
+        if _DEBUG_GRAPH:          # C2V_DEBUG_GRAPH=1: every replay is checked against an eager run of the same passes
+            eager = [self.model.apply_model(x, t, c, **kwargs) for c in conds]
+            dev = [float((o - e).abs().max() / e.abs().max()) for o, e in zip(g["outs"], eager)]
+            if max(dev) > 0:
+                print(f"[c2v debug] graph replay deviates from eager: {dev}", flush=True)
         return g["outs"]
 
     def _unet_pair(self, x, t, c, uc, kwargs, use_cuda_graph):

@@ -150,6 +150,49 @@ def test_small_step_without_guidance(small):
     assert rel(xp, xo)[0] < TOL_L2 and rel(p0, po)[0] < 2 * TOL_L2
 
 
+def test_graph_capture_with_saturated_pinned_caches(small):
+    """Regression (round 2): in a long-lived process the per-sample caches fill up with entries pinned by other graphs.  Eviction
+    then used to drop the entries the warm-up pass had just created, the capture re-created them INSIDE the graph on the first
+    branch, and the second (parallel) branch read them without a dependency edge - a full-size 25-step sample came out 1.7e-2 off
+    only when the whole suite ran in one process.  Now the entries a warm-up touches cannot be evicted, a capture that creates a
+    cache entry raises, and exactly the touched entries are pinned."""
+    from camc2v_b200 import modules as M
+    from camc2v_b200.sampler import DDIMSampler, DenoiserModel
+    cfg, unet, sd, g, inp, cam = small
+    keep = []
+    for i in range(70):                                       # more than every cache limit
+        pl = torch.randn(1, 64, 16, 2, 2, device=DEV)
+        cx = torch.randn(1, 77 + 256, cfg.context_dim, device=DEV)
+        M._pluker_cl(pl)
+        M.make_context_pack(cx, 16)
+        keep += [pl, cx]
+    token = M.pin_entries([e for cache in (M._PLUKER_CACHE, M._CONTEXT_CACHE) for e in cache.values()])
+    try:
+        model = DenoiserModel(unet).to(DEV)
+        s = DDIMSampler(model)
+        s.make_schedule(25, "uniform_trailing", 1.0, verbose=False)
+        ts = torch.full((1,), 599, dtype=torch.long, device=DEV)
+        noise = torch.randn(inp["x"].shape, generator=torch.Generator().manual_seed(5)).to(DEV)
+        cond = {"c_crossattn": [inp["ctx_cond"].to(DEV)], "c_concat": [inp["c_concat"].to(DEV)], "camera_condition": cam}
+        uc = {"c_crossattn": [inp["ctx_uncond"].to(DEV)], "c_concat": [inp["c_concat"].to(DEV)]}
+        kw = dict(unconditional_guidance_scale=3.5, unconditional_conditioning=uc, guidance_rescale=0.7, fs=inp["fs"].to(DEV),
+                  enable_camera_condition=True, noise=noise)
+        xe, pe = s.p_sample_ddim(inp["x"].to(DEV), cond, ts, index=14, **kw)
+        # (with saturated caches the eager step's own entries were evicted again: the warm-up re-creates them, protected by the
+        # recording; the sampler itself raises if the CAPTURE creates one)
+        xg, pg = s.p_sample_ddim(inp["x"].to(DEV), cond, ts, index=14, use_cuda_graph=True, **kw)
+        xg2, _ = s.p_sample_ddim(inp["x"].to(DEV), cond, ts, index=14, use_cuda_graph=True, **kw)
+        assert torch.equal(xg, xe) and torch.equal(pg, pe) and torch.equal(xg2, xe)
+        pinned = s._graph["pin"]
+        assert 0 < len(pinned) < 200 and all(id(e) in M._PINNED for e in pinned)
+        del s
+        import gc
+        gc.collect()
+        assert not any(id(e) in M._PINNED for e in pinned), "a dead sampler left its cache entries pinned"
+    finally:
+        M.unpin_caches(token)
+
+
 def test_sampling_loop_runs_and_is_deterministic(small):
     from camc2v_b200.sampler import DDIMSampler, DenoiserModel
     cfg, unet, sd, g, inp, cam = small
