@@ -219,11 +219,18 @@ int c2v_timestep_embedding(const int64_t* t, float* out, int n, int dim, void* s
 
 int c2v_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps, int silu,
                        void* stream) {
-    if (!x || !gamma || !beta || !out || !ws) return ERR_BAD_ARG;
+    if (!x || !gamma || !beta || !out) return ERR_BAD_ARG;       // ws may be NULL when c2v_groupnorm_kernels() == 1
     return groupnorm_silu_launch(x, gamma, beta, out, ws, ns, rows, C, eps, silu, (cudaStream_t)stream);
 }
 
 int64_t c2v_groupnorm_ws_floats(int ns, int rows, int C) { return groupnorm_ws_floats(ns, rows, C); }
+
+int c2v_groupnorm_kernels(int ns, int rows, int C) { return groupnorm_kernels(ns, rows, C); }
+
+int c2v_groupnorm_plan(int ns, int rows, int C, int* plan4) {
+    if (!plan4) return ERR_BAD_ARG;
+    return groupnorm_plan_debug(ns, rows, C, plan4, plan4 + 1, plan4 + 2, plan4 + 3) ? OK : ERR_UNSUPPORTED;
+}
 
 int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32, int rows,
                   int C, float eps, void* stream) {

@@ -163,8 +163,15 @@ def test_skinny_linear_and_timestep_embedding():
 
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("ns,rows,C,silu", [(16, 1024, 320, True), (1, 16384, 320, True), (16, 64, 1280, False), (16, 16, 2560, True),
-                                            (16, 256, 960, True), (2, 4096, 64, True), (16, 64, 1920, False)])
+                                            (16, 256, 960, True), (2, 4096, 64, True), (16, 64, 1920, False),
+                                            # round 2: every (slab, cluster) plan of the fused single-kernel path that the UNet uses
+                                            (1, 4096, 640, True), (1, 1024, 1280, False), (1, 256, 1280, True), (16, 16, 1280, True),
+                                            (16, 1024, 960, True), (16, 1024, 640, True), (16, 256, 1920, True), (4, 16384, 320, False),
+                                            (3, 1000, 320, True), (1, 1021, 640, False), (16, 4096, 512, True), (16, 65536, 128, True)])
 def test_groupnorm(ns, rows, C, silu):
+    """Shapes with C // 32 in (10, 30) have float4 columns that straddle two groups; (1, 16384, 320) / (1, 4096, 640) / ... are the
+    per-sample statistics of the temporal blocks (cluster of CTAs, DSMEM reduction); 1000 / 1021 rows are ragged slabs;
+    (2, 4096, 64) and (16, 65536, 128) have no single-kernel plan and take the statistics + apply pair."""
     ops = _ops()
     x = rnd(ns * rows, C, seed=1) * 3 + 0.5
     g = rnd(C, seed=2) * 0.1 + 1
