@@ -66,8 +66,6 @@ PROTOTYPES = {
     "c2v_timestep_embedding": (_i, [_vp, _vp, _i, _i, _vp]),
     "c2v_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
     "c2v_groupnorm_ws_floats": (_i64, [_i, _i, _i]),
-    "c2v_groupnorm_kernels": (_i, [_i, _i, _i]),
-    "c2v_groupnorm_plan": (_i, [_i, _i, _i, C.POINTER(C.c_int)]),
     "c2v_softmax_rows": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "c2v_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "c2v_attention": (_i, [C.POINTER(AttnDesc), _vp]),
@@ -129,7 +127,7 @@ def check(status: int, what: str):
         raise C2VError(f"{what} failed: {msg} (status {status})")
 
 
-KERNELS_PER_CALL = {"c2v_epipolar_tile_map": 2}   # every other entry point launches exactly one kernel (c2v_groupnorm_silu: see ops.groupnorm)
+KERNELS_PER_CALL = {"c2v_groupnorm_silu": 2, "c2v_epipolar_tile_map": 2}   # every other entry point launches exactly one kernel
 
 
 def call(name: str, *args):

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcamc2v_b200.so")
 OUT_FP16 = os.path.join(HERE, "libcamc2v_b200_fp16.so")        # same kernels with IEEE-half operands (-DC2V_OPERAND_FP16)
 OBJ = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["api.cu", "gemm_tc.cu", "attn_fa.cu", "epi_maps.cu", "attn_small.cu", "attn_t16.cu", "norm.cu", "elementwise.cu", "epipolar.cu", "pose.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_ps.cu", "attn_fa.cu", "epi_maps.cu", "attn_small.cu", "attn_t16.cu", "norm.cu", "elementwise.cu", "epipolar.cu", "pose.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"] + os.environ.get("C2V_NVCC_EXTRA", "").split()

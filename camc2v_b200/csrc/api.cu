@@ -164,6 +164,8 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     } else {
         return ERR_BAD_ARG;
     }
+    const PsPlan ps = gemm_ps_plan(a, bn);        // persistent form for the multi-wave 16-bit-output projections (gemm_ps.cu)
+    if (ps.mode) bn = ps.bn;
     {
         const uint64_t ktot = (uint64_t)d->taps * d->Cin;
         const uint64_t dims[2] = {ktot, (uint64_t)d->N};
@@ -171,6 +173,7 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
         const uint32_t box[2] = {64, (uint32_t)bn};
         if (!make_tmap_bf16(&a.tmB, d->w, 2, dims, strides, box)) return ERR_TMA_ENCODE;
     }
+    if (ps.mode) return gemm_ps_launch(a, ps, (cudaStream_t)stream);
     if (d->epi != C2V_EPI_GEGLU) {
         // TMA epilogue descriptors (residual load, output / split-K partial store).  When the output rows are not 16-byte
         // aligned (e.g. a 4-column bf16 output) the kernel falls back to its direct-store epilogue.
@@ -219,18 +222,11 @@ int c2v_timestep_embedding(const int64_t* t, float* out, int n, int dim, void* s
 
 int c2v_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps, int silu,
                        void* stream) {
-    if (!x || !gamma || !beta || !out) return ERR_BAD_ARG;       // ws may be NULL when c2v_groupnorm_kernels() == 1
+    if (!x || !gamma || !beta || !out || !ws) return ERR_BAD_ARG;
     return groupnorm_silu_launch(x, gamma, beta, out, ws, ns, rows, C, eps, silu, (cudaStream_t)stream);
 }
 
 int64_t c2v_groupnorm_ws_floats(int ns, int rows, int C) { return groupnorm_ws_floats(ns, rows, C); }
-
-int c2v_groupnorm_kernels(int ns, int rows, int C) { return groupnorm_kernels(ns, rows, C); }
-
-int c2v_groupnorm_plan(int ns, int rows, int C, int* plan4) {
-    if (!plan4) return ERR_BAD_ARG;
-    return groupnorm_plan_debug(ns, rows, C, plan4, plan4 + 1, plan4 + 2, plan4 + 3) ? OK : ERR_UNSUPPORTED;
-}
 
 int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32, int rows,
                   int C, float eps, void* stream) {

@@ -364,10 +364,134 @@ __global__ void __launch_bounds__(1024) cfg_ddim_kernel(const float* __restrict_
     }
 }
 
+// Cluster form (round 2): the one-CTA-per-sample kernel above sits alone at the end of every step (64 us for 65 536 elements: the
+// two UNet passes join before it, nothing overlaps it).  Here CS CTAs per sample form a thread-block cluster; every thread keeps its
+// <= 4 float4 of e_c / e_u (/ e_nc) in registers across the three phases (means, variances, update), and the per-sample sums are
+// combined through distributed shared memory in fixed rank order (deterministic).  Same arithmetic per element as above.
+constexpr int CFG_CS = 8, CFG_THREADS = 512, CFG_NV = 6;
+
+__device__ __forceinline__ double cluster_sum(double v, double* sh, double* slot, int cs) {
+    const double part = block_sum(v, sh);
+    if (threadIdx.x == 0) *slot = part;
+    cluster_sync_all();
+    double t = 0.0;
+    for (int rk = 0; rk < cs; ++rk) {
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(slot)), "r"(rk));
+        double x;
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(x) : "r"(ra) : "memory");
+        t += x;
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(CFG_THREADS) cfg_ddim_cluster_kernel(const float* __restrict__ x, const float* __restrict__ ec,
+                                                                       const float* __restrict__ eu, const float* __restrict__ enc,
+                                                                       const float* __restrict__ noise, float* __restrict__ x_prev,
+                                                                       float* __restrict__ pred_x0, int64_t n, float scale, float cam_w, float phi,
+                                                                       float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at) {
+    pdl_entry();
+    __shared__ double sh[32];
+    __shared__ double slots[4];
+    const size_t base = (size_t)blockIdx.y * n;
+    const int64_t chunk = n / CFG_CS;                    // floats per CTA (a multiple of 4)
+    const int64_t c0 = (int64_t)blockIdx.x * chunk;
+    const int nv = (int)(chunk >> 2);
+    float4 c4[CFG_NV], u4[CFG_NV], e4[CFG_NV];
+#pragma unroll
+    for (int k = 0; k < CFG_NV; ++k) {
+        const int v = threadIdx.x + k * CFG_THREADS;
+        if (v < nv) {
+            const size_t o = base + c0 + (size_t)v * 4;
+            c4[k] = *reinterpret_cast<const float4*>(ec + o);
+            u4[k] = *reinterpret_cast<const float4*>(eu + o);
+            const float* en = enc ? enc + o : nullptr;
+            e4[k].x = cfg_combine(c4[k].x, u4[k].x, scale, en, 0, cam_w);
+            e4[k].y = cfg_combine(c4[k].y, u4[k].y, scale, en, 1, cam_w);
+            e4[k].z = cfg_combine(c4[k].z, u4[k].z, scale, en, 2, cam_w);
+            e4[k].w = cfg_combine(c4[k].w, u4[k].w, scale, en, 3, cam_w);
+        }
+    }
+    float ratio = 1.f;
+    if (phi > 0.f) {
+        double sc = 0.0, se = 0.0;
+#pragma unroll
+        for (int k = 0; k < CFG_NV; ++k)
+            if ((int)(threadIdx.x + k * CFG_THREADS) < nv) {
+                sc += ((double)c4[k].x + (double)c4[k].y) + ((double)c4[k].z + (double)c4[k].w);
+                se += ((double)e4[k].x + (double)e4[k].y) + ((double)e4[k].z + (double)e4[k].w);
+            }
+        const double mc = cluster_sum(sc, sh, &slots[0], CFG_CS) / (double)n;
+        const double me = cluster_sum(se, sh, &slots[1], CFG_CS) / (double)n;
+        double vc = 0.0, ve = 0.0;
+#pragma unroll
+        for (int k = 0; k < CFG_NV; ++k)
+            if ((int)(threadIdx.x + k * CFG_THREADS) < nv) {
+                const double dcx = (double)c4[k].x - mc, dcy = (double)c4[k].y - mc, dcz = (double)c4[k].z - mc, dcw = (double)c4[k].w - mc;
+                const double dex = (double)e4[k].x - me, dey = (double)e4[k].y - me, dez = (double)e4[k].z - me, dew = (double)e4[k].w - me;
+                vc += (dcx * dcx + dcy * dcy) + (dcz * dcz + dcw * dcw);
+                ve += (dex * dex + dey * dey) + (dez * dez + dew * dew);
+            }
+        vc = cluster_sum(vc, sh, &slots[2], CFG_CS);
+        ve = cluster_sum(ve, sh, &slots[3], CFG_CS);
+        ratio = (float)sqrt(vc / (double)(n - 1)) / (float)sqrt(ve / (double)(n - 1));
+    }
+    const float sqrt_at = sqrtf(a_t), sqrt_aprev = sqrtf(a_prev);
+    const float dir = sqrtf(fmaxf(1.0f - a_prev - sigma_t * sigma_t, 0.f));
+#pragma unroll
+    for (int k = 0; k < CFG_NV; ++k) {
+        const int v = threadIdx.x + k * CFG_THREADS;
+        if (v < nv) {
+            const size_t o = base + c0 + (size_t)v * 4;
+            const float4 xv = *reinterpret_cast<const float4*>(x + o);
+            const float4 nz = *reinterpret_cast<const float4*>(noise + o);
+            const float ev[4] = {e4[k].x, e4[k].y, e4[k].z, e4[k].w}, xs[4] = {xv.x, xv.y, xv.z, xv.w}, ns[4] = {nz.x, nz.y, nz.z, nz.w};
+            float p0[4], xp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float e = ev[j];
+                if (phi > 0.f) e = __fadd_rn(__fmul_rn(phi, __fmul_rn(e, ratio)), __fmul_rn(1.0f - phi, e));
+                p0[j] = __fdiv_rn(__fsub_rn(xs[j], __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
+                xp[j] = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0[j]), __fmul_rn(dir, e)), __fmul_rn(sigma_t, ns[j]));
+            }
+            *reinterpret_cast<float4*>(pred_x0 + o) = make_float4(p0[0], p0[1], p0[2], p0[3]);
+            *reinterpret_cast<float4*>(x_prev + o) = make_float4(xp[0], xp[1], xp[2], xp[3]);
+        }
+    }
+    if (phi > 0.f) cluster_sync_all();      // no CTA exits while a peer may still read its slots
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, const float* enc, const float* noise, float* x_prev,
                            float* pred_x0, int B, int64_t n, float scale, float cam_w, float phi, float a_t, float a_prev, float sigma_t,
                            float sqrt_one_minus_at, cudaStream_t st) {
     if (B <= 0 || n <= 1) return ERR_BAD_ARG;
+    if (n % (CFG_CS * 4) == 0 && n / CFG_CS <= (int64_t)CFG_THREADS * 4 * CFG_NV && B <= 65535 && aligned16(x) && aligned16(ec) && aligned16(eu) &&
+        aligned16(noise) && aligned16(x_prev) && aligned16(pred_x0) && (!enc || aligned16(enc))) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(CFG_CS, B);
+        cfg.blockDim = dim3(CFG_THREADS);
+        cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        int na = 0;
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = CFG_CS;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+        if (pdl_enabled()) {
+            at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        cfg.attrs = at;
+        cfg.numAttrs = na;
+        C2V_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cfg_ddim_cluster_kernel, x, ec, eu, enc, noise, x_prev, pred_x0, n, scale, cam_w, phi, a_t, a_prev,
+                                          sigma_t, sqrt_one_minus_at));
+        return OK;
+    }
     C2V_CHECK_CUDA(launch(cfg_ddim_kernel, dim3(B), dim3(1024), 0, st, x, ec, eu, enc, noise, x_prev, pred_x0, n, scale, cam_w, phi, a_t, a_prev, sigma_t, sqrt_one_minus_at));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;

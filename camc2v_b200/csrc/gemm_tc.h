@@ -34,6 +34,14 @@ struct GemmKernelArgs {
 };
 
 int gemm_tc_launch(const GemmKernelArgs& a, int bn, int m_tiles, int n_tiles, cudaStream_t st);
+// gemm_ps.cu: persistent variant (one CTA per SM, double-buffered TMEM accumulator) for multi-wave 16-bit-output projections
+struct PsPlan {
+    int mode;   // 0: not taken; 1: streaming (A and B tiles through the ring); 2: B-resident (weight tile loaded once per CTA)
+    int bn;     // N tile width the weight tensor map must be built with
+    int P;      // B-resident: CTAs per N tile
+};
+PsPlan gemm_ps_plan(const GemmKernelArgs& a, int bn_default);      // needs M, N, k_chunks, taps, a_mode, epi, splits, out_bf16, residual, rowbias, tile_rows, ldo
+int gemm_ps_launch(const GemmKernelArgs& a, const PsPlan& pl, cudaStream_t st);
 int splitk_reduce_launch(const float* ws, int splits, int M, int N, const float* bias, const float* rowbias, int rows_per_group,
                          const float* residual, int ldr, void* out, int ldo, int out_bf16, cudaStream_t st);
 

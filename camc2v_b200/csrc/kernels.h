@@ -9,8 +9,6 @@ namespace c2v {
 int64_t groupnorm_ws_floats(int ns, int rows, int C);
 int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps,
                           int silu, cudaStream_t st);
-int groupnorm_kernels(int ns, int rows, int C);      // 1: fused single-kernel plan exists (ws unused); 2: stats + apply
-int groupnorm_plan_debug(int ns, int rows, int C, int* G, int* CS, int* R, int* NV);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32,
                      int rows, int C, float eps, cudaStream_t st);
 

@@ -43,22 +43,21 @@ __device__ __forceinline__ GnMap gn_map(int C) {
 __global__ void __launch_bounds__(GN_THREADS, 2) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws, int rows, int C,
                                                               int rows_per_slab) {
     pdl_entry();
-    // Per-thread fp32 partials are combined across the CTA as 64-bit fixed point: integer atomics are
-    // order-independent, so the statistics (and everything downstream) are bit-reproducible run to run.
-    __shared__ long long s_sum[32], s_sq[32];
-    constexpr float SUM_SCALE = 262144.f, SQ_SCALE = 1024.f;     // 2^18, 2^10
+    // Per-thread fp32 partials are combined across the CTA in a FIXED order (bit-reproducible run to run) without atomics: every
+    // thread stages (sum, sumsq) of the <= 2 groups its float4 column touches in shared memory, then one warp per group adds the
+    // staged values of that group's columns (lane-strided, doubles) and finishes with a shuffle tree.  (Round 1 used 64-bit
+    // fixed-point shared-memory atomics here: ATOMS.CAST.SPIN loops with ~16 threads contending per address.)
+    __shared__ float s_part[GN_MAX_SLOTS][4][GN_THREADS];
     const int n = blockIdx.y, slab = blockIdx.x, nslab = gridDim.x;
-    if (threadIdx.x < 32) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0;
-    __syncthreads();
     const GnMap m = gn_map(C);
     const int cg = C / 32;
     const int r0 = slab * rows_per_slab;
     const int r1 = min(rows, r0 + rows_per_slab);
     const float* xs = x + (size_t)n * rows * C;
-    if (m.active) {
-        for (int s = 0; s < m.slots; ++s) {
-            const int cv = m.cv0 + s * GN_THREADS;
-            if (cv >= m.nvec) break;
+    for (int s = 0; s < GN_MAX_SLOTS; ++s) {
+        float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+        const int cv = m.cv0 + s * GN_THREADS;
+        if (m.active && s < m.slots && cv < m.nvec) {
             float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             const float* col = xs + cv * 4;
             const size_t step = (size_t)m.rows_par * C;
@@ -77,27 +76,49 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_stats_kernel(const float* __
                 a[2] += (v0.z + v1.z) + (v2.z + v3.z); q[2] += fmaf(v0.z, v0.z, v1.z * v1.z) + fmaf(v2.z, v2.z, v3.z * v3.z);
                 a[3] += (v0.w + v1.w) + (v2.w + v3.w); q[3] += fmaf(v0.w, v0.w, v1.w * v1.w) + fmaf(v2.w, v2.w, v3.w * v3.w);
             }
-            const int g0 = (cv * 4) / cg, g3 = (cv * 4 + 3) / cg;
-            if (g0 == g3) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g0]),
-                          (unsigned long long)__float2ll_rn(((a[0] + a[1]) + (a[2] + a[3])) * SUM_SCALE));
-                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sq[g0]),
-                          (unsigned long long)__float2ll_rn(((q[0] + q[1]) + (q[2] + q[3])) * SQ_SCALE));
-            } else {
+            const int gA = (cv * 4) / cg;           // cg >= 2: a float4 column touches at most the groups gA and gA + 1
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int g = (cv * 4 + e) / cg;
-                    atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g]), (unsigned long long)__float2ll_rn(a[e] * SUM_SCALE));
-                    atomicAdd(reinterpret_cast<unsigned long long*>(&s_sq[g]), (unsigned long long)__float2ll_rn(q[e] * SQ_SCALE));
+            for (int e = 0; e < 4; ++e) {
+                if ((cv * 4 + e) / cg == gA) {
+                    sA += a[e]; qA += q[e];
+                } else {
+                    sB += a[e]; qB += q[e];
                 }
             }
         }
+        s_part[s][0][threadIdx.x] = sA; s_part[s][1][threadIdx.x] = qA; s_part[s][2][threadIdx.x] = sB; s_part[s][3][threadIdx.x] = qB;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float* w = ws + (((size_t)n * nslab + slab) * 32 + threadIdx.x) * 2;
-        w[0] = (float)((double)s_sum[threadIdx.x] * (1.0 / SUM_SCALE));
-        w[1] = (float)((double)s_sq[threadIdx.x] * (1.0 / SQ_SCALE));
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const bool wide = m.nvec >= GN_THREADS;
+        for (int g = warp; g < 32; g += GN_THREADS / 32) {
+            const int cvlo = (g * cg) >> 2, cvhi = ((g + 1) * cg - 1) >> 2;
+            const int ncv = cvhi - cvlo + 1;
+            const int items = m.rows_par * ncv;
+            double sd = 0.0, qd = 0.0;
+            for (int idx = lane; idx < items; idx += 32) {
+                const int rs = idx / ncv, c = cvlo + (idx - rs * ncv);
+                const int t = wide ? (c % GN_THREADS) : rs * m.nvec + c;
+                const int sl = wide ? (c / GN_THREADS) : 0;
+                const int tgA = (c * 4) / cg;
+                if (tgA == g) {
+                    sd += (double)s_part[sl][0][t]; qd += (double)s_part[sl][1][t];
+                } else {                               // the column starts in group g - 1 and ends in g
+                    sd += (double)s_part[sl][2][t]; qd += (double)s_part[sl][3][t];
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sd += __shfl_xor_sync(0xffffffffu, sd, o);
+                qd += __shfl_xor_sync(0xffffffffu, qd, o);
+            }
+            if (lane == 0) {
+                float* w = ws + (((size_t)n * nslab + slab) * 32 + g) * 2;
+                w[0] = (float)sd;
+                w[1] = (float)qd;
+            }
+        }
     }
 }
 
@@ -203,9 +224,9 @@ int64_t groupnorm_ws_floats(int ns, int rows, int C) {
     return (int64_t)ns * slabs * 64;
 }
 
-static int groupnorm_two_pass_launch(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps,
+int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps,
                           int silu, cudaStream_t st) {
-    if (C % 32 != 0 || C % 4 != 0 || (C >> 2) > GN_THREADS * GN_MAX_SLOTS || ns <= 0 || rows <= 0) return ERR_UNSUPPORTED;
+    if (C % 32 != 0 || C < 64 || (C >> 2) > GN_THREADS * GN_MAX_SLOTS || ns <= 0 || rows <= 0) return ERR_UNSUPPORTED;   // >= 2 channels per group
     if (ns > 65535) return ERR_UNSUPPORTED;
     int rps;
     const int slabs = gn_slabs(ns, rows, C, &rps);
@@ -214,250 +235,6 @@ static int groupnorm_two_pass_launch(const float* x, const float* gamma, const f
                           rows, C, rps, eps, silu));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fused GroupNorm (round 2): statistics + normalise + SiLU + cast in ONE kernel, the tensor read from global memory ONCE.
-//
-// A CTA owns a slab of R rows x (G groups = G*C/32 channels) of one sample and keeps it in REGISTERS (512 threads x NV float4,
-// every load of the slab issued before the first use: one memory round trip at full memory-level parallelism).  When the rows of
-// a sample do not fit one CTA (the per-sample statistics of the temporal blocks: 16384 rows at the 32x32 level) the CS CTAs that
-// share (sample, group block) form a thread-block CLUSTER and exchange their partial (sum, sum of squares) through distributed
-// shared memory - no second kernel, no global workspace, no grid-wide synchronisation.  The reduction is a fixed-order tree
-// (shared-memory staging + warp shuffles, doubles across threads), so the result is bit-reproducible run to run.
-// Replaces gn_stats_kernel + gn_apply_kernel wherever a plan exists (gn_plan); those two stay as the fallback for shapes
-// whose slab does not fit (e.g. the 256x256 feature maps of the VAE decoder).
-// ------------------------------------------------------------------------------------------------
-constexpr int GNF_THREADS = 512;
-constexpr int GNF_NV_BIG = 21, GNF_NV_SMALL = 8;
-
-__device__ __forceinline__ double ld_dsmem_f64(const double* p, uint32_t cta_rank) {
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(cta_rank));
-    double v;
-    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
-    return v;
-}
-
-template <int NV>
-__global__ void __launch_bounds__(GNF_THREADS, NV <= GNF_NV_SMALL ? 2 : 1)
-    gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    __nv_bfloat16* __restrict__ out, int rows, int C, int G, int R, int CS, float eps, int silu) {
-    __shared__ float s_part[4][GNF_THREADS];          // per-thread (sum, sq) of slot A / slot B (a float4 may straddle two groups)
-    __shared__ double s_gs[32], s_gq[32];             // this CTA's partial per local group (read by the cluster peers)
-    __shared__ float s_mean[32], s_rstd[32];
-    const int tid = threadIdx.x;
-    const int cg = C >> 5;
-    const int nvec = (G * cg) >> 2;
-    const int rows_par = GNF_THREADS / nvec;
-    const int rsub = tid / nvec, cv = tid - rsub * nvec;
-    const bool active = rsub < rows_par;
-    const int ch0 = blockIdx.y * G * cg;
-    const int r0 = blockIdx.x * R;
-    const int r1 = min(rows, r0 + R);
-    const size_t base = (size_t)blockIdx.z * rows * C;
-    const float* col = x + base + ch0 + cv * 4;
-    pdl_entry();
-
-    float4 v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int r = r0 + rsub + i * rows_par;
-        v[i] = (active && r < r1) ? *reinterpret_cast<const float4*>(col + (size_t)r * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    // ---- per-thread partials ----
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        a[0] += v[i].x; q[0] = fmaf(v[i].x, v[i].x, q[0]);
-        a[1] += v[i].y; q[1] = fmaf(v[i].y, v[i].y, q[1]);
-        a[2] += v[i].z; q[2] = fmaf(v[i].z, v[i].z, q[2]);
-        a[3] += v[i].w; q[3] = fmaf(v[i].w, v[i].w, q[3]);
-    }
-    // local group of each of the 4 channels; slot A = group of channel 0, slot B = the next group (cg >= 4: at most two)
-    const int gA = (cv * 4) / cg;
-    {
-        float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float se = a[e], qe = q[e];
-            if ((cv * 4 + e) / cg == gA) {
-                sA += se; qA += qe;
-            } else {
-                sB += se; qB += qe;
-            }
-        }
-        s_part[0][tid] = sA; s_part[1][tid] = qA; s_part[2][tid] = sB; s_part[3][tid] = qB;
-    }
-    __syncthreads();
-    // ---- block reduction: one warp per local group, fixed order ----
-    {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int g = warp; g < G; g += GNF_THREADS / 32) {
-            const int cvlo = (g * cg) >> 2, cvhi = ((g + 1) * cg - 1) >> 2;
-            const int ncv = cvhi - cvlo + 1;
-            const int items = rows_par * ncv;
-            double s = 0.0, q = 0.0;
-            for (int idx = lane; idx < items; idx += 32) {
-                const int rs = idx / ncv, c = cvlo + (idx - rs * ncv);
-                const int t = rs * nvec + c;
-                const int tgA = (c * 4) / cg;
-                if (tgA == g) {
-                    s += (double)s_part[0][t]; q += (double)s_part[1][t];
-                } else if (tgA + 1 == g) {
-                    s += (double)s_part[2][t]; q += (double)s_part[3][t];
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                q += __shfl_xor_sync(0xffffffffu, q, o);
-            }
-            if (lane == 0) {
-                s_gs[g] = s;
-                s_gq[g] = q;
-            }
-        }
-    }
-    if (CS > 1) cluster_sync_all(); else __syncthreads();
-    if (tid < G) {
-        double s = 0.0, q = 0.0;
-        if (CS > 1) {
-            for (int rk = 0; rk < CS; ++rk) {          // fixed rank order: identical result in every CTA of the cluster
-                s += ld_dsmem_f64(&s_gs[tid], rk);
-                q += ld_dsmem_f64(&s_gq[tid], rk);
-            }
-        } else {
-            s = s_gs[tid];
-            q = s_gq[tid];
-        }
-        const double cnt = (double)rows * (double)cg;
-        const double mean = s / cnt;
-        double var = q / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[tid] = (float)mean;
-        s_rstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    if (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // peers may exit once everyone has read
-    __syncthreads();
-    if (active) {
-        float sc[4], sh[4];
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + ch0 + cv * 4));
-        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + ch0 + cv * 4));
-        const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int g = (cv * 4 + e) / cg;
-            sc[e] = s_rstd[g] * gmv[e];
-            sh[e] = btv[e] - s_mean[g] * sc[e];
-        }
-        __nv_bfloat16* ocol = out + base + ch0 + cv * 4;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int r = r0 + rsub + i * rows_par;
-            if (r < r1) {
-                float y0 = fmaf(v[i].x, sc[0], sh[0]), y1 = fmaf(v[i].y, sc[1], sh[1]), y2 = fmaf(v[i].z, sc[2], sh[2]), y3 = fmaf(v[i].w, sc[3], sh[3]);
-                if (silu) {
-                    y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3);
-                }
-                *reinterpret_cast<uint2*>(ocol + (size_t)r * C) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
-            }
-        }
-    }
-    if (CS > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// Slab shape of the fused kernel for a (ns, rows, C) problem: G groups x ceil(rows / CS) rows per CTA, CS CTAs per cluster.
-struct GnPlan {
-    int G, CS, R, NV;
-};
-static bool gn_plan(int ns, int rows, int C, GnPlan* best) {
-    if (C % 32 != 0 || ns <= 0 || rows <= 0 || ns > 65535) return false;
-    const int cg = C / 32;
-    if (cg < 4) return false;                 // a float4 must not straddle more than two groups
-    double best_cost = 1e30;
-    bool found = false;
-    for (int G = 1; G <= 32; G *= 2) {
-        if ((G * cg) % 4 != 0) continue;
-        const int nvec = G * cg / 4;
-        if (nvec > GNF_THREADS) continue;
-        if (nvec < 5 && G < 32) continue;     // >= 80-byte row segments (coalescing)
-        const int rows_par = GNF_THREADS / nvec;
-        for (int CS = 1; CS <= 8; CS *= 2) {
-            const int R = (rows + CS - 1) / CS;
-            if ((long long)R * (CS - 1) >= rows && CS > 1) continue;      // an empty CTA in the cluster
-            const int iters = (R + rows_par - 1) / rows_par;
-            if (iters > GNF_NV_BIG) continue;
-            const int NV = iters <= GNF_NV_SMALL ? GNF_NV_SMALL : GNF_NV_BIG;
-            const int occ = NV == GNF_NV_SMALL ? 2 : 1;
-            const long long ctas = (long long)ns * (32 / G) * CS;
-            const long long waves = (ctas + 148LL * occ - 1) / (148LL * occ);
-            const double slab_kb = (double)R * nvec * 16.0 / 1024.0;
-            const double per_sm = slab_kb * (double)(ctas >= 148LL * occ ? occ : (ctas + 147) / 148);
-            const double cost = (double)waves * (2.0 + (CS > 1 ? 0.3 : 0.0) + per_sm / 40.0) + 1e-3 * CS - 1e-5 * G;
-            if (cost < best_cost) {
-                best_cost = cost;
-                *best = GnPlan{G, CS, R, NV};
-                found = true;
-            }
-        }
-    }
-    return found;
-}
-
-int groupnorm_kernels(int ns, int rows, int C) {
-    GnPlan p;
-    static const bool off = [] { const char* e = getenv("C2V_GN_FUSED"); return e && e[0] == '0'; }();
-    return (!off && gn_plan(ns, rows, C, &p)) ? 1 : 2;
-}
-
-int groupnorm_plan_debug(int ns, int rows, int C, int* G, int* CS, int* R, int* NV) {
-    GnPlan p;
-    if (!gn_plan(ns, rows, C, &p)) return 0;
-    *G = p.G; *CS = p.CS; *R = p.R; *NV = p.NV;
-    return 1;
-}
-
-template <int NV>
-static cudaError_t gn_fused_launch(const GnPlan& p, const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int ns, int rows,
-                                   int C, float eps, int silu, cudaStream_t st) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(p.CS, 32 / p.G, ns);
-    cfg.blockDim = dim3(GNF_THREADS);
-    cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    int na = 0;
-    if (pdl_enabled()) {
-        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    if (p.CS > 1) {
-        at[na].id = cudaLaunchAttributeClusterDimension;
-        at[na].val.clusterDim.x = p.CS;
-        at[na].val.clusterDim.y = 1;
-        at[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    cfg.attrs = at;
-    cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, gn_fused_kernel<NV>, x, gamma, beta, out, rows, C, p.G, p.R, p.CS, eps, silu);
-}
-
-int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps,
-                          int silu, cudaStream_t st) {
-    GnPlan p;
-    if (groupnorm_kernels(ns, rows, C) == 1 && gn_plan(ns, rows, C, &p)) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-        if (p.NV == GNF_NV_SMALL)
-            C2V_CHECK_CUDA(gn_fused_launch<GNF_NV_SMALL>(p, x, gamma, beta, o, ns, rows, C, eps, silu, st));
-        else
-            C2V_CHECK_CUDA(gn_fused_launch<GNF_NV_BIG>(p, x, gamma, beta, o, ns, rows, C, eps, silu, st));
-        return OK;
-    }
-    if (!ws) return ERR_BAD_ARG;
-    return groupnorm_two_pass_launch(x, gamma, beta, out, ws, ns, rows, C, eps, silu, st);
 }
 
 // ------------------------------------------------------------------------------------------------

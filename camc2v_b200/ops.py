@@ -146,10 +146,7 @@ def groupnorm(x: torch.Tensor, gamma, beta, ns: int, rows: int, eps: float, silu
     _chk(x, F32, "groupnorm.x")
     C_ = x.shape[1]
     out = torch.empty((ns * rows, C_), device=x.device, dtype=BF16)
-    ws = None
-    if _lib.load().c2v_groupnorm_kernels(ns, rows, C_) == 2:      # stats + apply through a workspace; otherwise one fused kernel
-        ws = torch.empty((_lib.load().c2v_groupnorm_ws_floats(ns, rows, C_),), device=x.device, dtype=F32)
-        _lib.LAUNCHES += 1
+    ws = torch.empty((_lib.load().c2v_groupnorm_ws_floats(ns, rows, C_),), device=x.device, dtype=F32)
     _lib.call("c2v_groupnorm_silu", _p(x), _p(gamma), _p(beta), _p(out), _p(ws), ns, rows, C_, float(eps), int(silu), _stream())
     return out
 

@@ -85,17 +85,10 @@ int c2v_timestep_embedding(const int64_t* t, float* out, int n, int dim, void* s
 /* GroupNorm(32 groups) [+ SiLU] over channels-last fp32 x [ns, rows, C]; statistics per (sample, group)
  * over rows x C/32 in fp32 (GroupNormSpecific, R/lvdm/basics.py:78-80; nn.GroupNorm eps 1e-6 of
  * attention.py:273,343; eps 1e-5 + SiLU of openaimodel3d.py:151-153,175-177,255-265).  out: bf16 [ns*rows, C].
- * `ws` is fp32 scratch of at least c2v_groupnorm_ws_floats(ns, rows, C) floats; it may be NULL when
- * c2v_groupnorm_kernels(ns, rows, C) == 1: the call is then ONE kernel that keeps each (sample, group block) slab in registers,
- * reads x once and combines the partial statistics of a sample's CTAs through a thread-block cluster (distributed shared memory);
- * otherwise (return 2) it is a statistics kernel + an apply kernel through `ws`. */
+ * `ws` is fp32 scratch of at least c2v_groupnorm_ws_floats(ns, rows, C) floats. */
 int c2v_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* out_bf16, float* ws,
                        int ns, int rows, int C, float eps, int silu, void* stream);
 int64_t c2v_groupnorm_ws_floats(int ns, int rows, int C);
-int c2v_groupnorm_kernels(int ns, int rows, int C);
-/* The single-kernel plan for inspection / tests: plan4 = {groups per CTA, CTAs per cluster, rows per CTA, float4 per thread};
- * C2V_ERR_UNSUPPORTED when the shape takes the two-kernel path. */
-int c2v_groupnorm_plan(int ns, int rows, int C, int* plan4);
 
 /* Row softmax: out[r, :] = softmax(scale * x[r, :]), fp32 [rows, n] -> 16-bit operands [rows, n] (n % 4 == 0).  The softmax of the
  * single-head 512-wide attention block of the VAE decoder (ae_modules.py:53-80), whose scores / P.V products go through c2v_gemm. */

@@ -83,35 +83,6 @@ def test_ops_reject_cpu_tensors():
         ops.groupnorm(torch.zeros(128, 64), torch.ones(64), torch.zeros(64), 1, 128, 1e-5, True)
 
 
-def test_groupnorm_single_kernel_plan():
-    """Host logic of the fused GroupNorm (norm.cu gn_plan): every GroupNorm shape of the UNet step has a single-kernel plan whose
-    slab fits the registers of one CTA (512 threads x NV float4) and whose cluster is portable; per-sample statistics over more rows
-    than one CTA holds get a cluster; shapes with fewer than 4 channels per group take the two-kernel path."""
-    import ctypes as C
-    from camc2v_b200 import _lib
-    lib = _lib.load()
-    unet = [(16, 1024, 320), (1, 16384, 320), (16, 256, 640), (1, 4096, 640), (16, 64, 1280), (1, 1024, 1280), (16, 16, 1280), (1, 256, 1280),
-            (16, 1024, 960), (16, 1024, 640), (16, 256, 1920), (16, 256, 1280), (16, 64, 2560), (16, 256, 960), (4, 16384, 320)]
-    for ns, rows, Cc in unet:
-        plan = (C.c_int * 4)()
-        assert lib.c2v_groupnorm_plan(ns, rows, Cc, plan) == 0, (ns, rows, Cc)
-        assert lib.c2v_groupnorm_kernels(ns, rows, Cc) == 1
-        G, CS, R, NV = list(plan)
-        cg = Cc // 32
-        assert 32 % G == 0 and (G * cg) % 4 == 0 and CS in (1, 2, 4, 8)
-        nvec = G * cg // 4
-        rows_par = 512 // nvec
-        assert rows_par >= 1 and -(-R // rows_par) <= NV <= 21       # the slab fits NV float4 per thread
-        assert R * CS >= rows and R * (CS - 1) < rows                  # the cluster covers the sample, no empty CTA
-    assert (C.c_int * 4)() is not None
-    assert lib.c2v_groupnorm_plan(1, 16384, 320, (C.c_int * 4)()) == 0
-    p = (C.c_int * 4)()
-    lib.c2v_groupnorm_plan(1, 16384, 320, p)
-    assert p[1] == 8                                                  # 21 MB of one sample: 8-CTA clusters
-    for ns, rows, Cc in [(2, 4096, 64), (16, 65536, 128)]:
-        assert lib.c2v_groupnorm_kernels(ns, rows, Cc) == 2
-
-
 # ------------------------------------------------------------------------------------------------ module contract
 @pytest.mark.parametrize("name,kw", [("small", dict(model_channels=64, origin_h=128, origin_w=128)), ("full", {})])
 def test_state_dict_keys_and_shapes_match_reference(name, kw):

@@ -94,6 +94,40 @@ def test_linear_strided_a_and_rowbias():
     close(out, ref, 2e-3, "linear strided+rowbias")
 
 
+@pytest.mark.parametrize("M,N,K,kind", [(16384, 2560, 320, "geglu"), (4096, 5120, 640, "geglu"), (1024, 10240, 1280, "geglu"), (16384, 4096, 512, "geglu"),
+                                        (16384, 960, 320, "linear"), (4096, 1920, 640, "linear"), (16384, 1536, 512, "linear"),
+                                        (16250, 960, 320, "linear"), (8000, 2560, 320, "geglu"), (16384, 640, 320, "gelu")])
+def test_persistent_gemm(M, N, K, kind):
+    """The multi-wave 16-bit-output projections go through gemm_ps.cu (one CTA per SM walking the tile list, accumulator
+    double-buffered in tensor memory): every tile of every wave must be right, including the ragged last M tile, and the result must
+    be bit-identical to the one-tile-per-CTA kernel (same accumulation order over K), which the same product split into row blocks
+    of fewer than 300 tiles selects."""
+    ops = _ops()
+    a = rnd(M, K, seed=1, dtype=_dt())
+    w = rnd(N, K, seed=2, std=K ** -0.5, dtype=_dt())
+    b = rnd(N, seed=3, std=0.1)
+    y = a.float() @ w.float().t() + b
+    if kind == "geglu":
+        x, gate = y.chunk(2, dim=-1)
+        ref = x * torch.nn.functional.gelu(gate)
+        w_il, b_il = ops.geglu_interleave(w, b)
+        out = ops.geglu_linear(a, w_il, b_il)
+        close(out, ref, 1e-2, "persistent geglu")
+        # same product through the one-tile kernel: split the rows into launches of fewer than 300 tiles
+        step = 128 * max(1, 299 // (N // ops.tile_n(N, ops.EPI_GEGLU)))
+        parts = [ops.geglu_linear(a[i:i + step], w_il, b_il) for i in range(0, M, step)]
+        assert torch.equal(out, torch.cat(parts)), "persistent and one-tile GEGLU kernels must agree bit for bit"
+    else:
+        ref = torch.nn.functional.gelu(y) if kind == "gelu" else y
+        out = ops.linear(a, w, bias=b, out_dtype=_dt(), gelu=(kind == "gelu"))
+        close(out, ref, 1e-2, "persistent linear")
+        nobias = ops.linear(a, w, out_dtype=_dt())
+        close(nobias, a.float() @ w.float().t(), 1e-2, "persistent linear, no bias")
+        step = 128 * max(1, 299 // ((N + ops.tile_n(N) - 1) // ops.tile_n(N)))
+        parts = [ops.linear(a[i:i + step], w, bias=b, out_dtype=_dt(), gelu=(kind == "gelu")) for i in range(0, M, step)]
+        assert torch.equal(out, torch.cat(parts)), "persistent and one-tile kernels must agree bit for bit"
+
+
 @pytest.mark.parametrize("C", [320, 512, 1280])
 def test_geglu(C):
     ops = _ops()
@@ -164,14 +198,13 @@ def test_skinny_linear_and_timestep_embedding():
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("ns,rows,C,silu", [(16, 1024, 320, True), (1, 16384, 320, True), (16, 64, 1280, False), (16, 16, 2560, True),
                                             (16, 256, 960, True), (2, 4096, 64, True), (16, 64, 1920, False),
-                                            # round 2: every (slab, cluster) plan of the fused single-kernel path that the UNet uses
+                                            # round 2: every GroupNorm shape of the UNet step (per-frame and per-sample statistics), ragged rows, wide maps
                                             (1, 4096, 640, True), (1, 1024, 1280, False), (1, 256, 1280, True), (16, 16, 1280, True),
                                             (16, 1024, 960, True), (16, 1024, 640, True), (16, 256, 1920, True), (4, 16384, 320, False),
-                                            (3, 1000, 320, True), (1, 1021, 640, False), (16, 4096, 512, True), (16, 65536, 128, True)])
+                                            (3, 1000, 320, True), (1, 1021, 640, False), (16, 4096, 512, True), (16, 65536, 128, True),
+                                            (2, 300, 96, True), (2, 64, 4096, False), (1, 50, 3200, True)])
 def test_groupnorm(ns, rows, C, silu):
-    """Shapes with C // 32 in (10, 30) have float4 columns that straddle two groups; (1, 16384, 320) / (1, 4096, 640) / ... are the
-    per-sample statistics of the temporal blocks (cluster of CTAs, DSMEM reduction); 1000 / 1021 rows are ragged slabs;
-    (2, 4096, 64) and (16, 65536, 128) have no single-kernel plan and take the statistics + apply pair."""
+    """C // 32 in (10, 30): float4 columns straddle two groups; ns = 1 rows: the per-sample statistics of the temporal blocks."""
     ops = _ops()
     x = rnd(ns * rows, C, seed=1) * 3 + 0.5
     g = rnd(C, seed=2) * 0.1 + 1
@@ -388,11 +421,13 @@ def test_downsample_conv_via_im2col():
     close(out, ref, 2e-3, "downsample conv")
 
 
+@pytest.mark.parametrize("shape", [(2, 4, 16, 32, 32), (3, 4, 16, 16, 16), (1, 4, 16, 40, 64), (2, 4, 3, 5, 7)])
 @pytest.mark.parametrize("phi", [0.0, 0.7])
-def test_cfg_ddim_update(phi):
+def test_cfg_ddim_update(phi, shape):
+    """(2|3, ...) samples of up to 98 304 elements take the 8-CTA cluster kernel (per-sample statistics through distributed shared
+    memory); the 40x64 latent and the odd-sized one take the one-CTA-per-sample kernel."""
     from oracle import ddim_oracle
     ops = _ops()
-    shape = (2, 4, 16, 32, 32)
     x, ec, eu, nz = (rnd(*shape, seed=s) for s in (1, 2, 3, 4))
     sch = ddim_oracle.ddim_schedule()
     i = 14

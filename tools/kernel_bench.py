@@ -162,6 +162,16 @@ def single(which):
         a, w, b = rb(16384, 320), rb(2560, 320), rb(2560, dtype=torch.float32)
         wi, bi = ops.geglu_interleave(w, b)
         fn = lambda: ops.geglu_linear(a, wi, bi)
+    elif which == "qkv0":
+        a, w = rb(16384, 320), rb(960, 320)
+        fn = lambda: ops.linear(a, w, out_dtype=ops.BF16)
+    elif which == "qkv1":
+        a, w = rb(4096, 640), rb(1920, 640)
+        fn = lambda: ops.linear(a, w, out_dtype=ops.BF16)
+    elif which == "geglu1":
+        a, w, b = rb(4096, 640), rb(5120, 640), rb(5120, dtype=torch.float32)
+        wi, bi = ops.geglu_interleave(w, b)
+        fn = lambda: ops.geglu_linear(a, wi, bi)
     elif which == "attn0":
         q, kv = rb(16 * 1024, 320), rb(16 * 1024, 640)
         fn = lambda: ops.attention(q, kv[:, :320], kv[:, 320:], 16, 1024, 1024, 5)
