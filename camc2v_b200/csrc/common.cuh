@@ -309,6 +309,32 @@ __device__ __forceinline__ float geglu_fast(float x, float g) {
     return fmaf(h, erfv, h);
 }
 __device__ __forceinline__ float gelu_erf_fast(float g) { return geglu_fast(1.0f, g); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// Two geglu_fast() at once on packed fp32 pairs (FFMA2 / FMUL2: one issue slot per pair for 11 of the 15 FMA-class operations; the
+// two MUFU operations, |g| and copysign stay scalar).  Same operation sequence per element as geglu_fast, with the polynomial
+// evaluated on negated coefficients (fma(-a, t, -b) == -fma(a, t, b) exactly), so the results are bit-identical to the scalar form.
+__device__ __forceinline__ float2 geglu_fast2(float2 x, float2 g) {
+    float2 t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(g.x), 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(g.y), 1.0f)));
+    float2 q = ffma2(make_float2(-1.061405429f, -1.061405429f), t, make_float2(1.453152027f, 1.453152027f));
+    q = ffma2(q, t, make_float2(-1.421413741f, -1.421413741f));
+    q = ffma2(q, t, make_float2(0.284496736f, 0.284496736f));
+    q = ffma2(q, t, make_float2(-0.254829592f, -0.254829592f));
+    q = fmul2(q, t);                                                   // = -poly(t) * t
+    const float2 ea = fmul2(fmul2(g, g), make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+    const float2 e = make_float2(fast_exp2(ea.x), fast_exp2(ea.y));
+    const float2 r = ffma2(q, e, make_float2(1.0f, 1.0f));             // 1 - poly * e
+    const float2 erfv = make_float2(copysignf(r.x, g.x), copysignf(r.y, g.y));
+    const float2 h = fmul2(fmul2(make_float2(0.5f, 0.5f), g), x);
+    return ffma2(h, erfv, h);
+}
 // ---- thread-block clusters: barrier + distributed shared memory ----
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -174,12 +174,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_ps_kernel(const _
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float y0 = geglu_fast(__uint_as_float(xv[4 * j]) + bx[j].x, __uint_as_float(gv[4 * j]) + bg[j].x);
-                        const float y1 = geglu_fast(__uint_as_float(xv[4 * j + 1]) + bx[j].y, __uint_as_float(gv[4 * j + 1]) + bg[j].y);
-                        const float y2 = geglu_fast(__uint_as_float(xv[4 * j + 2]) + bx[j].z, __uint_as_float(gv[4 * j + 2]) + bg[j].z);
-                        const float y3 = geglu_fast(__uint_as_float(xv[4 * j + 3]) + bx[j].w, __uint_as_float(gv[4 * j + 3]) + bg[j].w);
-                        pk[2 * j] = pack_bf16(y0, y1);
-                        pk[2 * j + 1] = pack_bf16(y2, y3);
+                        const float2 x01 = fadd2(make_float2(__uint_as_float(xv[4 * j]), __uint_as_float(xv[4 * j + 1])), make_float2(bx[j].x, bx[j].y));
+                        const float2 g01 = fadd2(make_float2(__uint_as_float(gv[4 * j]), __uint_as_float(gv[4 * j + 1])), make_float2(bg[j].x, bg[j].y));
+                        const float2 x23 = fadd2(make_float2(__uint_as_float(xv[4 * j + 2]), __uint_as_float(xv[4 * j + 3])), make_float2(bx[j].z, bx[j].w));
+                        const float2 g23 = fadd2(make_float2(__uint_as_float(gv[4 * j + 2]), __uint_as_float(gv[4 * j + 3])), make_float2(bg[j].z, bg[j].w));
+                        const float2 y01 = geglu_fast2(x01, g01), y23 = geglu_fast2(x23, g23);
+                        pk[2 * j] = pack_bf16(y01.x, y01.y);
+                        pk[2 * j + 1] = pack_bf16(y23.x, y23.y);
                     }
                     uint4* dst = reinterpret_cast<uint4*>(o + c);
                     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -306,8 +306,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 2) gemm_tc_kernel(const _
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 16; j += 2)
-                        pk[j / 2] = pack_bf16(geglu_fast(__uint_as_float(xv[j]) + bx[j], __uint_as_float(gv[j]) + bg[j]),
-                                              geglu_fast(__uint_as_float(xv[j + 1]) + bx[j + 1], __uint_as_float(gv[j + 1]) + bg[j + 1]));
+                    {
+                        const float2 y = geglu_fast2(fadd2(make_float2(__uint_as_float(xv[j]), __uint_as_float(xv[j + 1])), make_float2(bx[j], bx[j + 1])),
+                                                     fadd2(make_float2(__uint_as_float(gv[j]), __uint_as_float(gv[j + 1])), make_float2(bg[j], bg[j + 1])));
+                        pk[j / 2] = pack_bf16(y.x, y.y);
+                    }
                     uint4* dst = reinterpret_cast<uint4*>(o + c);
                     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
