@@ -122,7 +122,7 @@ def by_shape(model, sampler, cond, uc, static, recs):
             key = (f"gemm M={d.M} N={d.N} K={d.Cin * d.taps} taps={d.taps} epi={d.epi} res={int(bool(d.residual))} bf16={d.out_bf16} "
                    f"sk={max(1, d.splitk)}")
             fl = 2.0 * d.M * d.N * d.Cin * d.taps
-            log.append(("gemm_tc", key, fl))
+            log.append(("gemm_", key, fl))          # gemm_tc_kernel or gemm_ps_kernel (persistent)
             if d.splitk > 1 and d.ws:
                 log.append(("splitk_reduce", f"splitk_reduce M={d.M} N={d.N} sk={d.splitk}", 0.0))
         elif name == "c2v_attention":
