@@ -62,6 +62,7 @@ PROTOTYPES = {
     "c2v_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
     "c2v_gemm_tile_n": (_i, [_i, _i]),
     "c2v_gemm_splitk": (_i, [_i, _i, _i, _i, _i]),
+    "c2v_gemm_persistent_plan": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "c2v_skinny_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "c2v_timestep_embedding": (_i, [_vp, _vp, _i, _i, _vp]),
     "c2v_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),

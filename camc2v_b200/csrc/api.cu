@@ -64,6 +64,30 @@ int c2v_gemm_splitk(int M, int N, int Cin, int taps, int epi) {
     return s < 2 ? 1 : s;
 }
 
+int c2v_gemm_persistent_plan(int M, int N, int Cin, int epi, int out_bf16, int has_residual, int* plan3) {
+    if (!plan3 || M <= 0 || N <= 0 || Cin <= 0 || Cin % 64 != 0) return ERR_BAD_ARG;
+    const int bn = c2v_gemm_tile_n(N, epi);
+    if (bn == 0) return ERR_UNSUPPORTED;
+    GemmKernelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = M;
+    a.N = N;
+    a.k_chunks = Cin / 64;
+    a.taps = 1;
+    a.a_mode = A_PLAIN;
+    a.epi = epi;
+    a.out_bf16 = out_bf16;
+    a.residual = has_residual ? reinterpret_cast<const float*>(plan3) : nullptr;      // only tested for null-ness by the planner
+    a.ldo = epi == C2V_EPI_GEGLU ? N / 2 : N;
+    a.splits = c2v_gemm_splitk(M, N, Cin, 1, epi);
+    a.tile_rows = 128;
+    const PsPlan pl = gemm_ps_plan(a, bn);
+    plan3[0] = pl.mode;
+    plan3[1] = pl.mode ? pl.bn : bn;
+    plan3[2] = pl.P;
+    return OK;
+}
+
 int c2v_gemm(const c2v_gemm_desc* d, void* stream) {
     if (!d || !d->a || !d->w || !d->out) return ERR_BAD_ARG;
     if (d->M <= 0 || d->N <= 0 || d->Cin <= 0 || d->Cin % 64 != 0 || d->N % 4 != 0) return ERR_UNSUPPORTED;

@@ -71,6 +71,12 @@ int c2v_gemm(const c2v_gemm_desc* d, void* stream);
 int c2v_gemm_tile_n(int N, int epi);
 /* Split-K factor this library recommends for a GEMM (1 = none). */
 int c2v_gemm_splitk(int M, int N, int Cin, int taps, int epi);
+/* Which kernel form a plain linear (one tap, contiguous output) takes, for inspection / tests:
+ * plan3 = {mode, N tile, CTAs per N tile}; mode 0 = one output tile per CTA (gemm_tc.cu), 1 = persistent (one CTA per SM walks the
+ * tile list, accumulator double-buffered in tensor memory), 2 = persistent with the [N tile, K] weight tile resident in shared
+ * memory (gemm_ps.cu).  The persistent forms are taken by 16-bit-output products without residual and with >= 300 output tiles
+ * (the GEGLU and q|k|v projections of the 32x32 / 16x16 levels). */
+int c2v_gemm_persistent_plan(int M, int N, int Cin, int epi, int out_bf16, int has_residual, int* plan3);
 
 /* Small-M linear (time/fps embedding MLPs, ResBlock emb_layers; openaimodel3d.py:168-174, 370-380):
  * out[m,n] = sum_k act(in[m,k]) * w[n,k] + bias[n];  act = SiLU if silu_in.  in/out fp32, w bf16. */

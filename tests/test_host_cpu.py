@@ -83,6 +83,34 @@ def test_ops_reject_cpu_tensors():
         ops.groupnorm(torch.zeros(128, 64), torch.ones(64), torch.zeros(64), 1, 128, 1e-5, True)
 
 
+def test_persistent_gemm_plan():
+    """Host logic of gemm_ps.cu (gemm_ps_plan): the multi-wave 16-bit-output projections of the 32x32 / 16x16 levels go to the
+    persistent kernel - with the weight tile resident in shared memory where its whole K extent fits next to an A ring - and
+    everything with a residual, an fp32 result or fewer than 300 output tiles stays on the one-tile-per-CTA kernel."""
+    import ctypes as C
+    from camc2v_b200 import _lib
+    lib = _lib.load()
+
+    def plan(M, N, K, epi=0, bf16=1, res=0):
+        p = (C.c_int * 3)()
+        assert lib.c2v_gemm_persistent_plan(M, N, K, epi, bf16, res, p) == 0
+        return tuple(p)
+
+    GEGLU = _lib.EPI_GEGLU
+    assert plan(16384, 2560, 320, GEGLU) == (2, 256, 14)        # 160 KB weight tile + 4-stage A ring; 10 N tiles x 14 CTAs
+    assert plan(16384, 960, 320) == (2, 240, 37)                # q|k|v, 32x32 level: four 240-wide N tiles, 37 CTAs each
+    assert plan(4096, 1920, 640) == (2, 128, 9)                 # q|k|v, 16x16 level: K = 640 fits only a 128-wide tile
+    m, bn, _ = plan(4096, 5120, 640, GEGLU)                     # GEGLU weights are interleaved per 160-wide tile: 200 KB does not fit
+    assert (m, bn) == (1, 160)
+    assert plan(1024, 10240, 1280, GEGLU)[:2] == (1, 160)
+    for mode_bn_p in (plan(16384, 320, 320, bf16=0, res=1), plan(16384, 960, 320, bf16=0), plan(1024, 3840, 1280), plan(256, 1280, 1280)):
+        assert mode_bn_p[0] == 0                                 # residual / fp32 out / < 300 tiles
+    for M, N, K, epi in [(16384, 2560, 320, GEGLU), (16384, 960, 320, 0), (4096, 1920, 640, 0), (16384, 1536, 512, 0)]:
+        mode, bn, P = plan(M, N, K, epi)
+        if mode == 2:
+            assert N % bn == 0 and P * (N // bn) <= 148 and (K // 64) * bn * 128 + 3 * 16384 <= 226 * 1024
+
+
 # ------------------------------------------------------------------------------------------------ module contract
 @pytest.mark.parametrize("name,kw", [("small", dict(model_channels=64, origin_h=128, origin_w=128)), ("full", {})])
 def test_state_dict_keys_and_shapes_match_reference(name, kw):
