@@ -28,6 +28,7 @@ namespace {
 constexpr int PS_BM = 128;
 constexpr int PS_BK = 64;
 constexpr int PS_MAX_STAGES = 8;
+constexpr int PS_STAGE_OUT = 4 * 4096;        // linear epilogue: 32 rows x 128 B of staged output per epilogue warp
 }  // namespace
 
 // P == 0: streaming mode (A and B tiles through the ring); P > 0: B-resident mode with P CTAs per N tile.
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_ps_kernel(const _
     uint64_t* acc_empty = acc_full + 2;                           // [2] epilogue -> MMA: accumulator b has been read out
     uint64_t* b_bar = acc_empty + 2;                              // B-resident: the weight tile has landed
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_bar + 1);
+    uint8_t* stage_out = reinterpret_cast<uint8_t*>(full_bar) + 256;       // linear epilogue: 4 KB per epilogue warp (PS_STAGE_OUT)
 
     const int warp = threadIdx.x >> 5;
     // tile walk of this CTA: (first, step, end) over a linear index that is the tile number (streaming) or the M tile (B-resident)
@@ -196,40 +198,67 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_ps_kernel(const _
                     emit(c, xa, ga, bxa, bga);
                 }
             } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n0;
+                // Linear epilogue (EPI_WARPS == 4: one warp per TMEM lane quarter).  A lane owns a ROW of the accumulator, so storing
+                // from registers sends 32 different 128-byte lines per warp instruction, 16-32 bytes each (ncu on the first version:
+                // 26 % of the kernel's stall samples are the epilogue waiting to re-use registers that queued stores still hold).
+                // Instead the warp stages 64 columns (128 bytes per row, XOR-swizzled 16-byte units: conflict-free both ways) in its
+                // own 4 KB of shared memory and writes them back with 8 lanes per row: 4 full lines per store instruction.
+                static_assert(GEGLU || EPI_WARPS == 4, "the staged linear epilogue assumes one warp per lane quarter");
                 const float* bias_n = p.bias ? p.bias + n0 : nullptr;
                 const bool gelu = p.epi == EPI_GELU;
-                auto fetch = [&](int c, uint32_t (&v)[16], float4 (&bv)[4]) {
-                    tmem_ld16(trow + c, v);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) bv[j] = bias_n ? *reinterpret_cast<const float4*>(bias_n + c + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                };
-                auto emit = [&](int c, const uint32_t (&v)[16], const float4 (&bv)[4]) {
-                    if (!row_ok) return;
-                    float f[16];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        f[4 * j] = bv[j].x + __uint_as_float(v[4 * j]);
-                        f[4 * j + 1] = bv[j].y + __uint_as_float(v[4 * j + 1]);
-                        f[4 * j + 2] = bv[j].z + __uint_as_float(v[4 * j + 2]);
-                        f[4 * j + 3] = bv[j].w + __uint_as_float(v[4 * j + 3]);
-                    }
-                    if (gelu) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = gelu_erf_f(f[j]);
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(o + c);
-                    dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                    dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
-                };
-                uint32_t va[16];
-                float4 ba[4];
-                int c = grp * 16;                                         // 16-column chunks: BN = 240 is not a multiple of 32
+                uint8_t* wst = stage_out + (warp - 2) * 4096;
+                const int ln = lane_id();
+                const int rsw = ln & 7;                                     // this lane's row (= lane) modulo 8: swizzle key of its writes
+                __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(m_tile * PS_BM + lg * 32) * p.ldo + n0;
+                const int rows_ok = min(32, p.M - (m_tile * PS_BM + lg * 32));      // valid rows of this warp's slice (<= 0: none)
 #pragma unroll 1
-                for (; c < BN; c += CSTEP) {
-                    fetch(c, va, ba);
+                for (int c = 0; c < BN; c += 64) {
+                    uint32_t v[4][16];
+                    float4 bv[4][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (c + 16 * q < BN) {
+                            tmem_ld16(trow + c + 16 * q, v[q]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                bv[q][j] = bias_n ? *reinterpret_cast<const float4*>(bias_n + c + 16 * q + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
                     tmem_ld_wait();
-                    emit(c, va, ba);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (c + 16 * q < BN) {
+                            float f[16];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[4 * j] = bv[q][j].x + __uint_as_float(v[q][4 * j]);
+                                f[4 * j + 1] = bv[q][j].y + __uint_as_float(v[q][4 * j + 1]);
+                                f[4 * j + 2] = bv[q][j].z + __uint_as_float(v[q][4 * j + 2]);
+                                f[4 * j + 3] = bv[q][j].w + __uint_as_float(v[q][4 * j + 3]);
+                            }
+                            if (gelu) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) f[j] = gelu_erf_f(f[j]);
+                            }
+                            *reinterpret_cast<uint4*>(wst + ln * 128 + (((2 * q) ^ rsw) << 4)) =
+                                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                            *reinterpret_cast<uint4*>(wst + ln * 128 + (((2 * q + 1) ^ rsw) << 4)) =
+                                make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                        }
+                    }
+                    __syncwarp();
+                    const int u = ln & 7;                                   // 16-byte unit of the row this lane writes back
+                    if (c + u * 8 < BN) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + (ln >> 3);
+                            if (rr < rows_ok) {
+                                const uint4 val = *reinterpret_cast<const uint4*>(wst + rr * 128 + ((u ^ (rr & 7)) << 4));
+                                *reinterpret_cast<uint4*>(obase + (size_t)rr * p.ldo + c + u * 8) = val;
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
             // this warp has read its part of accumulator b: hand it back to the MMA warp
@@ -255,7 +284,8 @@ static int sm_count() {
 }
 
 constexpr int PS_SMEM_BUDGET = 226 * 1024;     // of the 227 KB an sm_100 CTA may use
-constexpr int PS_SMEM_FIXED = 256 + 1024;      // barriers / TMEM pointer + 1024-byte alignment slack
+constexpr int PS_SMEM_BASE = 256 + 1024;       // barriers / TMEM pointer + 1024-byte alignment slack
+constexpr int ps_fixed(bool geglu) { return PS_SMEM_BASE + (geglu ? 0 : PS_STAGE_OUT); }      // + the linear epilogue's staging
 
 template <int BN, int EPI_WARPS, bool GEGLU, bool BRES>
 static int ps_launch(const GemmKernelArgs& a, const PsPlan& pl, int m_tiles, cudaStream_t st) {
@@ -268,7 +298,7 @@ static int ps_launch(const GemmKernelArgs& a, const PsPlan& pl, int m_tiles, cud
     }
     GemmKernelArgs b = a;
     const int resident = BRES ? a.k_chunks * B_BYTES : 0;
-    int stages = (PS_SMEM_BUDGET - PS_SMEM_FIXED - resident) / STAGE_BYTES;
+    int stages = (PS_SMEM_BUDGET - ps_fixed(GEGLU) - resident) / STAGE_BYTES;
     if (stages > PS_MAX_STAGES) stages = PS_MAX_STAGES;
     if (stages < 2) return ERR_UNSUPPORTED;
     b.stages = stages;
@@ -276,7 +306,7 @@ static int ps_launch(const GemmKernelArgs& a, const PsPlan& pl, int m_tiles, cud
     const int tiles = m_tiles * n_tiles;
     const int grid = BRES ? pl.P * n_tiles : (tiles < sm_count() ? tiles : sm_count());
     C2V_CHECK_CUDA(launch(gemm_ps_kernel<BN, EPI_WARPS, GEGLU, BRES>, dim3(grid), dim3(64 + 32 * EPI_WARPS),
-                          (size_t)resident + (size_t)stages * STAGE_BYTES + PS_SMEM_FIXED, st, b, m_tiles, n_tiles, pl.P));
+                          (size_t)resident + (size_t)stages * STAGE_BYTES + ps_fixed(GEGLU), st, b, m_tiles, n_tiles, pl.P));
     return OK;
 }
 
@@ -305,7 +335,7 @@ PsPlan gemm_ps_plan(const GemmKernelArgs& a, int bn_default) {
             if (bn != 128 && bn != 160 && bn != 192 && bn != 240 && bn != 256) continue;
             if (a.N % bn != 0) continue;
             const int resident = a.k_chunks * bn * PS_BK * 2;
-            const int stages = (PS_SMEM_BUDGET - PS_SMEM_FIXED - resident) / (PS_BM * PS_BK * 2);
+            const int stages = (PS_SMEM_BUDGET - ps_fixed(a.epi == EPI_GEGLU) - resident) / (PS_BM * PS_BK * 2);
             if (stages < 3) continue;
             const int n_tiles = a.N / bn;
             if (n_tiles > sms) continue;
