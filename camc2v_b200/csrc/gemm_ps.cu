@@ -18,7 +18,8 @@
 // is chosen here (up to 256 wide, independent of gemm_tc's tile) to minimise the number of passes over A.
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2.. = epilogue (4 for the linear epilogue, 8 for the
-// erf GEGLU epilogue: two warps per TMEM lane quarter, even / odd 16-column chunks).
+// erf GEGLU epilogue: two warps per TMEM lane quarter, lower / upper half of the tile's output columns).  A lane owns an accumulator
+// ROW, so both epilogues stage their 16-bit results per warp in shared memory and write them back with several lanes per row.
 #include "common.cuh"
 #include "gemm_tc.h"
 
@@ -28,7 +29,7 @@ namespace {
 constexpr int PS_BM = 128;
 constexpr int PS_BK = 64;
 constexpr int PS_MAX_STAGES = 8;
-constexpr int PS_STAGE_OUT = 4 * 4096;        // linear epilogue: 32 rows x 128 B of staged output per epilogue warp
+constexpr int PS_STAGE_OUT = 4 * 4096;        // staged output: 4 KB per warp (linear epilogue, 4 warps) / 2 KB per warp (GEGLU, 8 warps)
 }  // namespace
 
 // P == 0: streaming mode (A and B tiles through the ring); P > 0: B-resident mode with P CTAs per N tile.
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_ps_kernel(const _
     uint64_t* acc_empty = acc_full + 2;                           // [2] epilogue -> MMA: accumulator b has been read out
     uint64_t* b_bar = acc_empty + 2;                              // B-resident: the weight tile has landed
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_bar + 1);
-    uint8_t* stage_out = reinterpret_cast<uint8_t*>(full_bar) + 256;       // linear epilogue: 4 KB per epilogue warp (PS_STAGE_OUT)
+    uint8_t* stage_out = reinterpret_cast<uint8_t*>(full_bar) + 256;       // epilogue staging (PS_STAGE_OUT bytes)
 
     const int warp = threadIdx.x >> 5;
     // tile walk of this CTA: (first, step, end) over a linear index that is the tile number (streaming) or the M tile (B-resident)
@@ -140,27 +141,21 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_ps_kernel(const _
         }
     } else {
         // ===================== epilogue =====================
-        const int lg = warp & 3;                       // TMEM lane quarter this warp may access
-        const int r = lg * 32 + lane_id();
+        const int lg = warp & 3;                       // TMEM lane quarter this warp may access (lane = accumulator row)
         const int grp = (warp - 2) >> 2;               // 0 / 1: which of the two warps of this lane quarter (EPI_WARPS == 8)
-        constexpr int NGRP = EPI_WARPS / 4;
         int i = 0;
         for (int tile = t_first; tile < t_end; tile += t_step, ++i) {
             const int m_tile = BRES ? tile : tile / n_tiles, n_tile = BRES ? n_fixed : tile - m_tile * n_tiles;
             const int b = i & 1;
-            const int m = m_tile * PS_BM + r;
-            const bool row_ok = m < p.M;
             const int n0 = n_tile * BN;
             mbar_wait(&acc_full[b], (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)b * ACC_STRIDE;
-            // 16-column chunks, chunk k of this warp at column grp * 16 + k * CSTEP: load -> wait -> compute -> store.  (A register
-            // double buffer that keeps the tcgen05.ld of chunk k+1 in flight under the math of chunk k, and 16 instead of 8 epilogue
-            // warps, were both measured in-step and gave nothing: profiles/r02i_ab_ps_variants.txt.)
-            constexpr int CSTEP = 16 * NGRP;
+            // 16-column chunks: tcgen05.ld -> wait -> compute -> stage in shared memory -> coalesced write-back.  (A register double
+            // buffer that keeps the tcgen05.ld of chunk k+1 in flight under the math of chunk k, 16 instead of 8 epilogue warps and
+            // four chunks per wait were all measured and gave nothing: profiles/r02i_ab_ps_variants.txt, r02o_ab_*.)
             if constexpr (GEGLU) {
                 constexpr int HALF = BN / 2;
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n_tile * HALF;
                 const float* bias_x = p.bias ? p.bias + n0 : nullptr;
                 auto fetch = [&](int c, uint32_t (&xv)[16], uint32_t (&gv)[16], float4 (&bx)[4], float4 (&bg)[4]) {
                     tmem_ld16(trow + c, xv);
@@ -171,8 +166,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_ps_kernel(const _
                         bg[j] = bias_x ? *reinterpret_cast<const float4*>(bias_x + HALF + c + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 };
-                auto emit = [&](int c, const uint32_t (&xv)[16], const uint32_t (&gv)[16], const float4 (&bx)[4], const float4 (&bg)[4]) {
-                    if (!row_ok) return;
+                // Staged write-back (see the linear epilogue below): the two warps of a lane quarter take the lower / upper half of the
+                // tile's output chunks; a warp stages two chunks (32 columns = 64 B per row, XOR-swizzled 16-byte units) in its own 2 KB
+                // and writes them back with 4 lanes per row - 8 rows x 64 B per store instruction instead of 32 rows x 32 B.
+                constexpr int NCH = HALF / 16, C0 = (NCH + 1) / 2;
+                const int ch_lo = grp == 0 ? 0 : C0, ch_hi = grp == 0 ? C0 : NCH;
+                uint8_t* wst = stage_out + (warp - 2) * 2048;
+                const int ln = lane_id();
+                __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(m_tile * PS_BM + lg * 32) * p.ldo + n_tile * HALF;
+                const int rows_ok = min(32, p.M - (m_tile * PS_BM + lg * 32));
+                auto stage = [&](int slot, const uint32_t (&xv)[16], const uint32_t (&gv)[16], const float4 (&bx)[4], const float4 (&bg)[4]) {
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -184,18 +187,36 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_ps_kernel(const _
                         pk[2 * j] = pack_bf16(y01.x, y01.y);
                         pk[2 * j + 1] = pack_bf16(y23.x, y23.y);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(o + c);
-                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    const int sw = (ln >> 1) & 3;
+                    *reinterpret_cast<uint4*>(wst + ln * 64 + (((2 * slot) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(wst + ln * 64 + (((2 * slot + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 };
                 uint32_t xa[16], ga[16];
                 float4 bxa[4], bga[4];
-                int c = grp * 16;
 #pragma unroll 1
-                for (; c < HALF; c += CSTEP) {
-                    fetch(c, xa, ga, bxa, bga);
+                for (int ch = ch_lo; ch < ch_hi; ch += 2) {
+                    const bool two = ch + 1 < ch_hi;
+                    fetch(ch * 16, xa, ga, bxa, bga);
                     tmem_ld_wait();
-                    emit(c, xa, ga, bxa, bga);
+                    stage(0, xa, ga, bxa, bga);
+                    if (two) {
+                        fetch(ch * 16 + 16, xa, ga, bxa, bga);
+                        tmem_ld_wait();
+                        stage(1, xa, ga, bxa, bga);
+                    }
+                    __syncwarp();
+                    const int u = ln & 3;
+                    if (u < (two ? 4 : 2)) {
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int rr = it * 8 + (ln >> 2);
+                            if (rr < rows_ok) {
+                                const uint4 val = *reinterpret_cast<const uint4*>(wst + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
+                                *reinterpret_cast<uint4*>(obase + (size_t)rr * p.ldo + ch * 16 + u * 8) = val;
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             } else {
                 // Linear epilogue (EPI_WARPS == 4: one warp per TMEM lane quarter).  A lane owns a ROW of the accumulator, so storing
@@ -285,7 +306,7 @@ static int sm_count() {
 
 constexpr int PS_SMEM_BUDGET = 226 * 1024;     // of the 227 KB an sm_100 CTA may use
 constexpr int PS_SMEM_BASE = 256 + 1024;       // barriers / TMEM pointer + 1024-byte alignment slack
-constexpr int ps_fixed(bool geglu) { return PS_SMEM_BASE + (geglu ? 0 : PS_STAGE_OUT); }      // + the linear epilogue's staging
+constexpr int ps_fixed(bool) { return PS_SMEM_BASE + PS_STAGE_OUT; }      // + the epilogue's staging (both epilogues)      // + the linear epilogue's staging
 
 template <int BN, int EPI_WARPS, bool GEGLU, bool BRES>
 static int ps_launch(const GemmKernelArgs& a, const PsPlan& pl, int m_tiles, cudaStream_t st) {
