@@ -68,9 +68,9 @@ PROTOTYPES = {
     "c2v_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
     "c2v_groupnorm_ws_floats": (_i64, [_i, _i, _i]),
     "c2v_softmax_rows": (_i, [_vp, _vp, _i, _i, _f, _vp]),
-    "c2v_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "c2v_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "c2v_attention": (_i, [C.POINTER(AttnDesc), _vp]),
-    "c2v_attention_temporal": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "c2v_attention_temporal": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_attention_temporal_hd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "c2v_pixel_unshuffle_cl": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "c2v_avgpool2_cl": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

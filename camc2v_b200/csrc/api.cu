@@ -253,9 +253,9 @@ int c2v_groupnorm_silu(const float* x, const float* gamma, const float* beta, vo
 int64_t c2v_groupnorm_ws_floats(int ns, int rows, int C) { return groupnorm_ws_floats(ns, rows, C); }
 
 int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32, int rows,
-                  int C, float eps, void* stream) {
-    if (!x || !gamma || !beta || !out) return ERR_BAD_ARG;
-    return layernorm_launch(x, gamma, beta, out, add, out2, out_f32, rows, C, eps, (cudaStream_t)stream);
+                  int C, float eps, int ld_out2, void* stream) {
+    if (!x || !gamma || !beta || !out || ld_out2 < 0) return ERR_BAD_ARG;
+    return layernorm_launch(x, gamma, beta, out, add, out2, out_f32, rows, C, eps, ld_out2, (cudaStream_t)stream);
 }
 
 int c2v_epipolar_tile_map_words(int T, int H, int W);
@@ -335,9 +335,9 @@ int c2v_attention(const c2v_attn_desc* d, void* stream) {
     return attn_fa_launch(a, (d->lq + 127) / 128, d->heads, d->bq, (cudaStream_t)stream);
 }
 
-int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int heads, void* stream) {
-    if (!qkv || !out || B <= 0 || HW <= 0 || heads <= 0) return ERR_BAD_ARG;
-    return attention_temporal_launch(qkv, out, B, T, HW, heads, (cudaStream_t)stream);
+int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int heads, int ldo, void* stream) {
+    if (!qkv || !out || B <= 0 || HW <= 0 || heads <= 0 || ldo < 0) return ERR_BAD_ARG;
+    return attention_temporal_launch(qkv, out, B, T, HW, heads, ldo, (cudaStream_t)stream);
 }
 
 int c2v_attention_temporal_hd(const void* qkv, void* out, int B, int T, int HW, int heads, int head_dim, void* stream) {

@@ -16,7 +16,7 @@ constexpr int TA_LD = 66;   // padded row stride in bf16 elements (33 words: con
 
 template <int T>
 __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                                      int B, int HW, int heads) {
+                                                                      int B, int HW, int heads, int ldo) {
     pdl_entry();
     constexpr int G = 32 / T;          // lanes sharing one query row
     constexpr int KPL = T / G;         // keys per lane
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(const __nv
         }
     }
     const size_t orow = ((size_t)b * T + i) * HW + pix;
-    __nv_bfloat16* o = out + orow * C + head * 64 + h * DPL;
+    __nv_bfloat16* o = out + orow * ldo + head * 64 + h * DPL;
 #pragma unroll
     for (int d = 0; d < DPL; d += 8)
         *reinterpret_cast<uint4*>(o + d) = make_uint4(pack_bf16(acc[d], acc[d + 1]), pack_bf16(acc[d + 2], acc[d + 3]),
@@ -134,7 +134,7 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 }
 
 __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal16_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                                            int B, int HW, int heads) {
+                                                                            int B, int HW, int heads, int ldo) {
     pdl_entry();
     constexpr int T = 16;
     __shared__ __align__(16) __nv_bfloat16 sm[TA_WARPS][3][T][TM_LD];
@@ -212,18 +212,20 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal16_mma_kernel(cons
     for (int t0 = 0; t0 < T; t0 += 4) {
         const int t = t0 + (lane >> 3);
         const size_t orow = ((size_t)b * T + t) * HW + pix;
-        *reinterpret_cast<uint4*>(out + orow * C + head * 64 + (lane & 7) * 8) = *reinterpret_cast<const uint4*>(&sm[warp][0][t][(lane & 7) * 8]);
+        *reinterpret_cast<uint4*>(out + orow * ldo + head * 64 + (lane & 7) * 8) = *reinterpret_cast<const uint4*>(&sm[warp][0][t][(lane & 7) * 8]);
     }
 }
 
-int attention_temporal_launch(const void* qkv, void* out, int B, int T, int HW, int heads, cudaStream_t st) {
+int attention_temporal_launch(const void* qkv, void* out, int B, int T, int HW, int heads, int ldo, cudaStream_t st) {
+    if (ldo == 0) ldo = heads * 64;
+    if (ldo < heads * 64 || ldo % 8 != 0) return ERR_UNSUPPORTED;      // 16-byte row stores
     const int64_t total = (int64_t)B * HW * heads;
     const int grid = (int)((total + TA_WARPS - 1) / TA_WARPS);
     const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     switch (T) {
-        case 8: C2V_CHECK_CUDA(launch(attn_temporal_kernel<8>, dim3(grid), dim3(TA_WARPS * 32), 0, st, q, o, B, HW, heads)); break;
-        case 16: C2V_CHECK_CUDA(launch(attn_temporal16_mma_kernel, dim3(grid), dim3(TA_WARPS * 32), 0, st, q, o, B, HW, heads)); break;
+        case 8: C2V_CHECK_CUDA(launch(attn_temporal_kernel<8>, dim3(grid), dim3(TA_WARPS * 32), 0, st, q, o, B, HW, heads, ldo)); break;
+        case 16: C2V_CHECK_CUDA(launch(attn_temporal16_mma_kernel, dim3(grid), dim3(TA_WARPS * 32), 0, st, q, o, B, HW, heads, ldo)); break;
         default: return ERR_UNSUPPORTED;
     }
     C2V_CHECK_CUDA(cudaGetLastError());

@@ -10,7 +10,7 @@ int64_t groupnorm_ws_floats(int ns, int rows, int C);
 int groupnorm_silu_launch(const float* x, const float* gamma, const float* beta, void* out, float* ws, int ns, int rows, int C, float eps,
                           int silu, cudaStream_t st);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32,
-                     int rows, int C, float eps, cudaStream_t st);
+                     int rows, int C, float eps, int ld2, cudaStream_t st);
 
 int softmax_rows_launch(const float* x, void* out, int rows, int n, float scale, cudaStream_t st);
 
@@ -30,7 +30,7 @@ int cfg_ddim_update_launch(const float* x, const float* ec, const float* eu, con
                            float sqrt_one_minus_at, cudaStream_t st);
 
 // attn_t16.cu
-int attention_temporal_launch(const void* qkv, void* out, int B, int T, int HW, int heads, cudaStream_t st);
+int attention_temporal_launch(const void* qkv, void* out, int B, int T, int HW, int heads, int ldo, cudaStream_t st);
 
 // pose.cu
 int pixel_unshuffle_cl_launch(const float* in, void* out, int B, int C, int T, int H, int W, int r, cudaStream_t st);

@@ -248,7 +248,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ add, __nv_bfloat16* __restrict__ out2,
-                                                        float* __restrict__ out_f32, int rows, int C, float eps) {
+                                                        float* __restrict__ out_f32, int rows, int C, float eps, int ld2) {
     pdl_entry();
     const int wpb = blockDim.x >> 5, stride = gridDim.x * wpb;
     int row = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                 if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * C + cv * 4) = make_float4(y0, y1, y2, y3);
                 if (add) {
                     const float4 p = *reinterpret_cast<const float4*>(add + (size_t)row * C + cv * 4);
-                    *reinterpret_cast<uint2*>(out2 + (size_t)row * C + cv * 4) =
+                    *reinterpret_cast<uint2*>(out2 + (size_t)row * ld2 + cv * 4) =
                         make_uint2(pack_bf16(y0 + p.x, y1 + p.y), pack_bf16(y2 + p.z, y3 + p.w));
                 }
             }
@@ -312,8 +312,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, const float* add, void* out2, float* out_f32,
-                     int rows, int C, float eps, cudaStream_t st) {
+                     int rows, int C, float eps, int ld2, cudaStream_t st) {
     if (C % 4 != 0 || (C >> 2) > LN_MAXV * 32 || rows <= 0) return ERR_UNSUPPORTED;
+    if (ld2 == 0) ld2 = C;
+    if (ld2 < C || ld2 % 4 != 0) return ERR_UNSUPPORTED;      // 8-byte stores into out2
     if (add && !out2) return ERR_BAD_ARG;
     const int nv = ((C >> 2) + 31) / 32;
     // few rows: 4-warp CTAs, one row per warp, spread over all SMs; many rows: 8-warp CTAs, 4 per SM, each warp walking its rows
@@ -323,11 +325,11 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(out2);
     if (nv <= 3)
-        C2V_CHECK_CUDA(launch(layernorm_kernel<3>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps));
+        C2V_CHECK_CUDA(launch(layernorm_kernel<3>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps, ld2));
     else if (nv <= 5)
-        C2V_CHECK_CUDA(launch(layernorm_kernel<5>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps));
+        C2V_CHECK_CUDA(launch(layernorm_kernel<5>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps, ld2));
     else
-        C2V_CHECK_CUDA(launch(layernorm_kernel<LN_MAXV>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps));
+        C2V_CHECK_CUDA(launch(layernorm_kernel<LN_MAXV>, dim3(grid), dim3(wpb * 32), 0, st, x, gamma, beta, o, add, o2, out_f32, rows, C, eps, ld2));
     C2V_CHECK_CUDA(cudaGetLastError());
     return OK;
 }

@@ -484,11 +484,14 @@ class CrossAttention(_Prepared):
         o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], bq, lq, lq, self.heads)
         return ops.linear(o, p["wo"], bias=p["bo"], residual=residual, out_dtype=out_dtype)
 
+    def temporal_heads(self, n: torch.Tensor, dm: Dims, out: Optional[torch.Tensor] = None):
+        """The attention output BEFORE to_out (bf16 [B*T*HW, heads*64]); `out` may be a column block of a wider buffer."""
+        qkv = ops.linear(n, self.pk()["wqkv"], out_dtype=BF16)
+        return ops.attention_temporal(qkv, dm.B, dm.T, dm.HW, self.heads, out=out)
+
     def self_temporal(self, n: torch.Tensor, dm: Dims, residual, out_dtype=F32):
         p = self.pk()
-        qkv = ops.linear(n, p["wqkv"], out_dtype=BF16)
-        o = ops.attention_temporal(qkv, dm.B, dm.T, dm.HW, self.heads)
-        return ops.linear(o, p["wo"], bias=p["bo"], residual=residual, out_dtype=out_dtype)
+        return ops.linear(self.temporal_heads(n, dm), p["wo"], bias=p["bo"], residual=residual, out_dtype=out_dtype)
 
     def _context_kv(self, ctx: "ContextPack", w: torch.Tensor, slot: str):
         """K|V projection of the text / image context tokens.  The context is a per-sample constant (it does not depend on
@@ -643,6 +646,11 @@ class EpipolarCrossAttention(_Prepared):
     def forward_cl(self, src: torch.Tensor, dm: Dims, cam: CameraLevel, residual, out_dtype=F32):
         """src bf16 CL [B*T*HW, C] (self epipolar attention: context == x, epipolar.py:141-143)."""
         p = self.pk()
+        return ops.linear(self.heads_cl(src, dm, cam), p["wo"], bias=p["bo"], residual=residual, out_dtype=out_dtype)
+
+    def heads_cl(self, src: torch.Tensor, dm: Dims, cam: CameraLevel, out: Optional[torch.Tensor] = None):
+        """The attention output BEFORE to_out (bf16 [B*T*HW, heads*64]); `src` and `out` may be column blocks of a wider buffer."""
+        p = self.pk()
         C = self.heads * 64
         L = dm.T * dm.HW
         qkv = ops.linear(src, p["wqkv"], out_dtype=BF16)
@@ -655,8 +663,7 @@ class EpipolarCrossAttention(_Prepared):
                       epi_bitmask=_bitmask(cam.F, dm.T, dm.H, dm.W, cam.d) if USE_EPI_BITMASK else None)
         elif cam.mask is not None:
             kw = dict(mask=cam.mask)
-        o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], dm.B, L, L, self.heads, k2=k2, v2=v2, **kw)
-        return ops.linear(o, p["wo"], bias=p["bo"], residual=residual, out_dtype=out_dtype)
+        return ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], dm.B, L, L, self.heads, k2=k2, v2=v2, out=out, **kw)
 
     def forward(self, x, context=None, attn_mask=None):
         """Reference signature (efficient_forward): x [B, L1, C], context [B, L2, C], attn_mask bool [B, L1, L2]."""
@@ -756,7 +763,24 @@ class BasicTransformerBlock(_RefBindable, _Prepared):
             if hasattr(self, name):
                 lin = getattr(self, name)
                 p[name] = (_bf16(lin.weight), _f32(lin.bias))
+        src = self._fused_out_sources()
+        if src is not None:
+            # z = pluker_projection(n + p) + Epipolar(n + p) ; x = z + attn1(n) + x (modified_forwards.py:519-533) are three
+            # Linear layers summed into the stream: one GEMM over the K-concatenated operand [n + p | attn1 heads | epipolar heads]
+            # with the weights side by side and the biases added up — one read-modify-write of the fp32 stream instead of three.
+            p["w_cat"] = _bf16(torch.cat([l.weight for l in src], dim=1))
+            p["b_cat"] = _f32(sum(l.bias.detach().float() for l in src))
+            p["cat_ver"] = tuple((id(t), t._version) for l in src for t in (l.weight, l.bias))
         return p
+
+    def _fused_out_sources(self):
+        """The three output projections of the camera-conditioned temporal block, when all are present with equal shapes."""
+        if not FUSE_TEMPORAL_OUT or self.variant != "camcontext" or not hasattr(self, "epipolar") or not hasattr(self, "pluker_projection"):
+            return None
+        src = (self.pluker_projection, self.attn1.to_out[0], self.epipolar.epipolar_attn.to_out[0])
+        if any(l.weight.shape != src[0].weight.shape or l.bias is None for l in src):
+            return None
+        return src
 
     def add_module(self, name, module):
         """The reference injects camera sub-modules into the temporal blocks by name (`epipolar`, `pluker_projection`,
@@ -790,6 +814,19 @@ class BasicTransformerBlock(_RefBindable, _Prepared):
         if cam is not None and (has_epi or has_pp) and self.variant == "camcontext":
             if cam.add_type != "add_to_main_branch":
                 raise NotImplementedError("only add_type == 'add_to_main_branch' (the shipped configs) is implemented")
+            if "w_cat" in p and cam.pluker is not None:
+                fs = self._fused_out_sources()
+                if p["cat_ver"] != tuple((id(t), t._version) for l in fs for t in (l.weight, l.bias)):
+                    self._pk = None                                                 # a child's parameters were rewritten in place
+                    p = self.pk()
+                C = x.shape[1]
+                cat = torch.empty((x.shape[0], 3 * C), device=x.device, dtype=BF16)
+                n, src = ops.layernorm(x, p["g1"], p["b1"], add=cam.pluker, out2=cat[:, :C])                # n + p
+                self.attn1.temporal_heads(n, dm, out=cat[:, C:2 * C])
+                self.epipolar.epipolar_attn.heads_cl(src, dm, cam, out=cat[:, 2 * C:])
+                x = ops.linear(cat, p["w_cat"], bias=p["b_cat"], residual=x)        # x + pp(n + p) + attn1(n) + Epipolar(n + p)
+                x = self.attn2.self_temporal(ops.layernorm(x, p["g2"], p["b2"]), dm, residual=x)
+                return self.ff.forward_cl(ops.layernorm(x, p["g3"], p["b3"]), residual=x, out_dtype=BF16)
             if cam.pluker is not None:
                 n, src = ops.layernorm(x, p["g1"], p["b1"], add=cam.pluker)
             else:
@@ -863,6 +900,7 @@ def _pad_cols(w: torch.Tensor, mult: int):
 # (torch bumps `_version`) is recomputed INTO THE SAME BUFFER, so pointers captured in a CUDA graph stay valid; callers that
 # replay a graph after refilling static conditioning buffers call `refresh_camera_caches()` first.
 USE_EPI_BITMASK = os.environ.get("C2V_EPI_BITMASK", "1") != "0"      # packed per-sample mask cache (A/B switch)
+FUSE_TEMPORAL_OUT = os.environ.get("C2V_TT_FUSE", "1") != "0"        # one K-concatenated GEMM for the temporal block's three output projections (A/B switch)
 _PLUKER_CACHE: Dict[tuple, list] = {}
 _TILEMAP_CACHE: Dict[tuple, list] = {}
 _BITMASK_CACHE: Dict[tuple, list] = {}

@@ -161,14 +161,24 @@ def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:
     return out
 
 
-def layernorm(x: torch.Tensor, gamma, beta, add: Optional[torch.Tensor] = None, eps: float = 1e-5, want_f32: bool = False):
-    """Returns LN(x) in bf16; with `add` also LN(x)+add (bf16); with want_f32 also the un-rounded fp32 LN(x) (last)."""
+def layernorm(x: torch.Tensor, gamma, beta, add: Optional[torch.Tensor] = None, eps: float = 1e-5, want_f32: bool = False,
+              out2: Optional[torch.Tensor] = None):
+    """Returns LN(x) in bf16; with `add` also LN(x)+add (bf16; written into `out2` when given: a [rows, C] view whose row stride
+    may exceed C); with want_f32 also the un-rounded fp32 LN(x) (last)."""
     _chk(x, F32, "layernorm.x")
     rows, C_ = x.shape
     out = torch.empty((rows, C_), device=x.device, dtype=BF16)
-    out2 = torch.empty_like(out) if add is not None else None
+    if add is None:
+        out2 = None
+    elif out2 is None:
+        out2 = torch.empty_like(out)
+    else:
+        _chk(out2, BF16, "layernorm.out2")
+        if tuple(out2.shape) != (rows, C_) or out2.stride(1) != 1:
+            raise _lib.C2VError("layernorm.out2 must be a [rows, C] view with unit column stride")
     of = torch.empty((rows, C_), device=x.device, dtype=F32) if want_f32 else None
-    _lib.call("c2v_layernorm", _p(x), _p(gamma), _p(beta), _p(out), _p(add), _p(out2), _p(of), rows, C_, float(eps), _stream())
+    _lib.call("c2v_layernorm", _p(x), _p(gamma), _p(beta), _p(out), _p(add), _p(out2), _p(of), rows, C_, float(eps),
+              out2.stride(0) if out2 is not None else 0, _stream())
     res = (out,) + ((out2,) if add is not None else ()) + ((of,) if want_f32 else ())
     return res if len(res) > 1 else out
 
@@ -208,11 +218,17 @@ def attention(q, k, v, bq: int, lq: int, lk: int, heads: int, kv_div: int = 1, o
     return out
 
 
-def attention_temporal(qkv: torch.Tensor, B: int, T: int, HW: int, heads: int):
-    """qkv bf16 [B*T*HW, 3*heads*64] (q | k | v) -> bf16 [B*T*HW, heads*64]; attention over T per (b, pixel)."""
+def attention_temporal(qkv: torch.Tensor, B: int, T: int, HW: int, heads: int, out: Optional[torch.Tensor] = None):
+    """qkv bf16 [B*T*HW, 3*heads*64] (q | k | v) -> bf16 [B*T*HW, heads*64]; attention over T per (b, pixel).  `out` may be a
+    column block of a wider buffer (row stride > heads*64)."""
     _chk(qkv, BF16, "attention_temporal.qkv")
-    out = torch.empty((B * T * HW, heads * 64), device=qkv.device, dtype=BF16)
-    _lib.call("c2v_attention_temporal", _p(qkv), _p(out), B, T, HW, heads, _stream())
+    if out is None:
+        out = torch.empty((B * T * HW, heads * 64), device=qkv.device, dtype=BF16)
+    else:
+        _chk(out, BF16, "attention_temporal.out")
+        if tuple(out.shape) != (B * T * HW, heads * 64) or out.stride(1) != 1:
+            raise _lib.C2VError("attention_temporal.out must be a [B*T*HW, heads*64] view with unit column stride")
+    _lib.call("c2v_attention_temporal", _p(qkv), _p(out), B, T, HW, heads, out.stride(0), _stream())
     return out
 
 

@@ -103,9 +103,11 @@ int c2v_softmax_rows(const float* x, void* out_bf16, int rows, int n, float scal
 /* LayerNorm over the last dim (nn.LayerNorm, attention.py:232-234), fp32 in -> bf16 out.  If `add` is not
  * NULL a second output out2 = LN(x) + add is produced (normed_x + pluker features,
  * R/model/modules/modified_forwards.py:508-520); add is fp32 [rows, C].  out_f32 (optional) receives the
- * un-rounded normalised rows (CameraCtrl adds cc_projection(...) to them, cameractrl_modified_modules.py:235-239). */
+ * un-rounded normalised rows (CameraCtrl adds cc_projection(...) to them, cameractrl_modified_modules.py:235-239).
+ * ld_out2: row stride of out2 in elements (0 = C; a multiple of 4) — the temporal block writes LN(x) + pluker straight into its
+ * column block of the K-concatenated operand of the fused output projection (see c2v_attention_temporal). */
 int c2v_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, const float* add, void* out2_bf16,
-                  float* out_f32, int rows, int C, float eps, void* stream);
+                  float* out_f32, int rows, int C, float eps, int ld_out2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention.
@@ -144,8 +146,11 @@ typedef struct c2v_attn_desc {
 int c2v_attention(const c2v_attn_desc* d, void* stream);
 
 /* Temporal self-attention over T <= 32 frames per pixel (attention.py:105-129 with q=k=v of length T):
- * qkv bf16 [B, T, HW, 3*heads*64] packed (q | k | v), out bf16 [B, T, HW, heads*64]. */
-int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int heads, void* stream);
+ * qkv bf16 [B, T, HW, 3*heads*64] packed (q | k | v), out bf16 [B, T, HW, heads*64] with row stride ldo elements (0 = heads*64;
+ * a multiple of 8).  A stride wider than the row lets the caller collect several attention outputs side by side: the
+ * camera-conditioned temporal block (modified_forwards.py:505-536) sums pluker_projection(n + p), Epipolar(n + p).to_out and
+ * attn1(n).to_out into the stream, which is ONE c2v_gemm over the K-concatenated operand [n + p | attn1 | epipolar]. */
+int c2v_attention_temporal(const void* qkv, void* out, int B, int T, int HW, int heads, int ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera pose encoder (SURVEY f-2; CamContextI2V/model/modules/camera_pose_encoder.py:295-376): the ops the UNet path does

@@ -229,6 +229,12 @@ def test_layernorm(rows, C):
     o1, o2 = ops.layernorm(x, g, b, add=add)
     close(o1, ref, 6e-3, "layernorm.1")
     close(o2, ref + add, 6e-3, "layernorm.2")
+    # the second output written into a column block of a wider buffer (the temporal block's K-concatenated operand)
+    wide = torch.full((rows, 3 * C), 7.0, device=DEV, dtype=_dt())
+    o1s, o2s = ops.layernorm(x, g, b, add=add, out2=wide[:, C:2 * C])
+    assert o2s.data_ptr() == wide[:, C:2 * C].data_ptr()
+    assert torch.equal(o1s, o1) and torch.equal(wide[:, C:2 * C], o2), "strided out2 must be bit-identical"
+    assert (wide[:, :C] == 7).all() and (wide[:, 2 * C:] == 7).all(), "strided out2 wrote outside its column block"
 
 
 # ------------------------------------------------------------------------------------------------ attention
@@ -343,6 +349,10 @@ def test_attention_temporal(B, T, HW, heads):
     x = qkv.view(B, T, HW, 3, C).permute(3, 0, 2, 1, 4).reshape(3, B * HW, T, C)
     ref = ref_attention(x[0], x[1], x[2], heads).view(B, HW, T, C).permute(0, 2, 1, 3).reshape(B * T * HW, C)
     close(out, ref, 1e-2, "temporal attention")
+    wide = torch.full((B * T * HW, 3 * C), 7.0, device=DEV, dtype=_dt())
+    ops.attention_temporal(qkv, B, T, HW, heads, out=wide[:, 2 * C:])
+    assert torch.equal(wide[:, 2 * C:], out), "strided output must be bit-identical"
+    assert (wide[:, :2 * C] == 7).all(), "strided output wrote outside its column block"
 
 
 # ------------------------------------------------------------------------------------------------ camera (bit-exact)

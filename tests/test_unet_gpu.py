@@ -282,6 +282,62 @@ def test_module_forwards_reference_layout_vs_oracle(small):
     assert rel(y, y_ref)[0] < 1e-2
 
 
+def test_fused_temporal_projection_equals_the_three_separate_ones(small, monkeypatch):
+    """x + pluker_projection(n + p) + attn1(n) + Epipolar(n + p) (modified_forwards.py:519-533) as ONE GEMM over the K-concatenated
+    operand [n + p | attn1 heads | epipolar heads] against the three residual GEMMs it replaces (C2V_TT_FUSE=0)."""
+    from camc2v_b200 import modules, ops
+    cfg, unet, sd, g, inp, cam = small
+    # (1) the product itself: same fp32 result up to summation order
+    gen = torch.Generator().manual_seed(11)
+    M, C = 2048, 320
+    cat = torch.randn(M, 3 * C, generator=gen).to(DEV).to(ops.BF16)
+    ws = [(torch.randn(C, C, generator=gen) * 0.05).to(DEV).to(ops.BF16) for _ in range(3)]
+    bs = [torch.randn(C, generator=gen).to(DEV) for _ in range(3)]
+    x = torch.randn(M, C, generator=gen).to(DEV)
+    y3 = x
+    for i in range(3):
+        y3 = ops.linear(cat[:, i * C:(i + 1) * C], ws[i], bias=bs[i], residual=y3)
+    y1 = ops.linear(cat, torch.cat(ws, dim=1).contiguous(), bias=bs[0] + bs[1] + bs[2], residual=x)
+    assert rel(y1, y3)[1] < 1e-5, rel(y1, y3)
+    # (2) the pass: both forms within the stated tolerance of the reference's golden output.  (They differ from EACH OTHER at the
+    # 16-bit rounding-noise level, ~1.3e-3: a 1e-7 change of the fp32 stream re-rolls the operand roundings of every later layer.)
+    xc = torch.cat([inp["x"], inp["c_concat"]], dim=1).to(DEV)
+    t = torch.full((1,), 599, dtype=torch.long, device=DEV)
+    run = lambda: unet(xc, t, context=inp["ctx_cond"].to(DEV), fs=inp["fs"].to(DEV), camera_condition=cam)
+    fused_blocks = lambda: [m for m in unet.modules() if isinstance(m, modules.BasicTransformerBlock) and "w_cat" in (m._pk or {})]
+    gold = torch.from_numpy(g["y_cond"])
+    assert modules.FUSE_TEMPORAL_OUT
+    unet.invalidate()
+    y_f = run()
+    blocks = fused_blocks()
+    n_cam = sum(1 for m in unet.modules() if isinstance(m, modules.BasicTransformerBlock) and hasattr(m, "epipolar"))
+    assert n_cam > 0 and len(blocks) == n_cam, "every camera-conditioned temporal block takes the fused projection"
+    assert max(rel(y_f, gold)) < TOL_L2
+    blk = blocks[0]
+    w = blk.attn1.to_out[0].weight
+    Cb = w.shape[0]
+    try:
+        monkeypatch.setattr(modules, "FUSE_TEMPORAL_OUT", False)
+        unet.invalidate()
+        y_s = run()
+        assert not fused_blocks()
+        assert max(rel(y_s, gold)) < TOL_L2 and max(rel(y_f, y_s)) < TOL_L2, (rel(y_s, gold), rel(y_f, y_s))
+        # (3) a child module's parameters rewritten in place are picked up by the block-level pack without invalidate()
+        monkeypatch.setattr(modules, "FUSE_TEMPORAL_OUT", True)
+        unet.invalidate()
+        assert torch.equal(run(), y_f)
+        with torch.no_grad():
+            w.mul_(2.0)
+        run()
+        assert torch.equal(blk._pk["w_cat"][:, Cb:2 * Cb], w.detach().to(ops.BF16)), "stale fused weight pack"
+    finally:
+        with torch.no_grad():
+            name = [k for k, v in unet.named_modules() if v is blk][0]
+            w.copy_(sd[name + ".attn1.to_out.0.weight"])
+        monkeypatch.undo()
+        unet.invalidate()
+
+
 def test_fp16_range_of_the_residual_stream(small):
     """The fp32 residual stream is unnormalised; a real checkpoint can push it past the largest finite half (65504).  Its only
     16-bit consumers are the ResBlock 1x1 skip convolution (cast of h / of the skip concat): that copy is stored at 2^-8 with the
