@@ -44,7 +44,7 @@ def rb(*shape, dtype=None):
 def bench_gemm():
     print("== linear: M K N  [out dtype, residual]")
     shapes = [
-        (16384, 320, 320, "f32", True), (16384, 320, 960, "bf16", False), (16384, 1280, 320, "f32", True),
+        (16384, 320, 320, "f32", True), (16384, 960, 320, "f32", True), (16384, 320, 960, "bf16", False), (16384, 1280, 320, "f32", True),
         (4096, 640, 640, "f32", True), (4096, 640, 1920, "bf16", False), (4096, 2560, 640, "f32", True),
         (1024, 1280, 1280, "f32", True), (1024, 1280, 3840, "bf16", False), (1024, 5120, 1280, "f32", True),
         (256, 1280, 1280, "f32", True), (256, 5120, 1280, "f32", True), (768, 1024, 2560, "bf16", False), (77, 1024, 640, "bf16", False),
@@ -131,6 +131,9 @@ def single(which):
     from camc2v_b200 import camera, synth
     if which == "lin0":
         a, w, b, r = rb(16384, 320), rb(320, 320), rb(320, dtype=torch.float32), rb(16384, 320, dtype=torch.float32)
+        fn = lambda: ops.linear(a, w, bias=b, residual=r)
+    elif which == "lincat0":        # the temporal block's fused output projection: K-concatenated [n + p | attn1 | epipolar], 32x32 level
+        a, w, b, r = rb(16384, 960), rb(320, 960), rb(320, dtype=torch.float32), rb(16384, 320, dtype=torch.float32)
         fn = lambda: ops.linear(a, w, bias=b, residual=r)
     elif which == "conv0":
         a, w, b, r = rb(16384, 320), rb(320, 2880), rb(320, dtype=torch.float32), rb(16384, 320, dtype=torch.float32)
