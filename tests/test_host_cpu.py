@@ -126,6 +126,42 @@ def test_state_dict_keys_and_shapes_match_reference(name, kw):
         assert abs(n / 1e6 - 1500.9) < 0.1        # 1500.9 M parameters
 
 
+def test_temporal_block_fused_projection_pack(monkeypatch):
+    """Host logic of the fused output projection of the camera-conditioned temporal block (modified_forwards.py:519-533):
+    x + pluker_projection(n + p) + attn1(n).to_out + Epipolar(n + p).to_out == [n + p | attn1 heads | epipolar heads] @ w_cat^T + b_cat + x."""
+    from camc2v_b200 import modules, synth
+    from camc2v_b200.config import UNetConfig
+    from camc2v_b200.modules import build_unet
+    unet = build_unet(UNetConfig(model_channels=64, origin_h=128, origin_w=128))
+    synth.fill_module_(unet, seed=0)
+    blocks = [m for m in unet.modules() if isinstance(m, modules.BasicTransformerBlock) and hasattr(m, "epipolar")]
+    assert len(blocks) == 16                                      # SURVEY a9: 16 temporal blocks carry epipolar + pluker_projection
+    blk = blocks[3]
+    p = blk._prepare()
+    pp, a1, ep = blk.pluker_projection, blk.attn1.to_out[0], blk.epipolar.epipolar_attn.to_out[0]
+    C = pp.weight.shape[0]
+    assert tuple(p["w_cat"].shape) == (C, 3 * C) and p["w_cat"].dtype == modules.BF16 and p["w_cat"].is_contiguous()
+    for i, lin in enumerate((pp, a1, ep)):
+        assert torch.equal(p["w_cat"][:, i * C:(i + 1) * C], lin.weight.detach().to(modules.BF16))
+    assert torch.allclose(p["b_cat"], (pp.bias + a1.bias + ep.bias).detach().float())
+    g = torch.Generator().manual_seed(0)
+    cat = torch.randn(40, 3 * C, generator=g)
+    three = sum(torch.nn.functional.linear(cat[:, i * C:(i + 1) * C], lin.weight.float(), lin.bias.float()) for i, lin in enumerate((pp, a1, ep)))
+    one = cat @ torch.cat([pp.weight, a1.weight, ep.weight], dim=1).float().t() + p["b_cat"]
+    assert torch.allclose(one, three, atol=1e-5)
+    # parameters of a CHILD module rewritten in place change the key the forward compares
+    key = lambda: tuple((id(t), t._version) for l in blk._fused_out_sources() for t in (l.weight, l.bias))
+    assert p["cat_ver"] == key()
+    with torch.no_grad():
+        a1.weight.mul_(2.0)
+    assert p["cat_ver"] != key()
+    # blocks without the injected camera modules, the other variants and the A/B switch keep the three-GEMM form
+    plain = [m for m in unet.modules() if isinstance(m, modules.BasicTransformerBlock) and not hasattr(m, "epipolar")]
+    assert plain and all("w_cat" not in m._prepare() for m in plain[:2])
+    monkeypatch.setattr(modules, "FUSE_TEMPORAL_OUT", False)
+    assert "w_cat" not in blk._prepare()
+
+
 def test_topology_matches_reference_ds_lists():
     from camc2v_b200.config import UNetConfig, build_topology
     topo = build_topology(UNetConfig())
