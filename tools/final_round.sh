@@ -11,7 +11,7 @@ timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke OK')
 timeout 400 python bench.py 2>gpurun_out/${tag}_bench.err | tail -1 > gpurun_out/${tag}_bench_line.json
 timeout 600 python bench.py --impl reference --steps ${REF_STEPS:-5} --warmup ${REF_WARMUP:-2} 2>/dev/null | tail -1 > gpurun_out/${tag}_reference_line.json
 timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_step.csv python tools/one_step.py > gpurun_out/${tag}_one_step.log 2>&1
-for spec in "epi0map attn_fa_kernel" "attn0 attn_fa_kernel" "lin0 gemm_tc_kernel" "conv0 gemm_tc_kernel" "geglu0 gemm_ps_kernel" "qkv0 gemm_ps_kernel" "gn0 gn_apply_kernel"; do
+for spec in "epi0map attn_fa_kernel" "attn0 attn_fa_kernel" "lin0 gemm_tc_kernel" "lincat0 gemm_tc_kernel" "conv0 gemm_tc_kernel" "geglu0 gemm_ps_kernel" "qkv0 gemm_ps_kernel" "gn0 gn_apply_kernel"; do
   set -- $spec
   timeout 200 ncu --set full --clock-control none --import-source on -k regex:$2 -s 3 -c 1 -f -o gpurun_out/${tag}_prof_$1 python tools/kernel_bench.py single $1 > gpurun_out/${tag}_prof_$1.log 2>&1
 done
